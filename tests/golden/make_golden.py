@@ -1,0 +1,259 @@
+"""Generate golden vectors by running the REAL reference (vlad17/runlmc).
+
+Run in the build container only (the reference checkout is not present on the
+GPU box):
+
+    PYTHONPATH=/root/reference PYTHONDONTWRITEBYTECODE=1 OMP_NUM_THREADS=1 \
+        python tests/golden/make_golden.py
+
+It imports the unmodified reference modules, feeds them seeded inputs and
+stores inputs and outputs in ``tests/golden/*.npz``.  The only accommodations
+(SURVEY.md section 8c):
+  * scipy >= 1.14 renamed minres' ``tol`` to ``rtol``; approx/iterative.py:50
+    still passes ``tol=`` -> a keyword shim is installed here.
+  * lmc/functional_kernel.py needs paramz (absent); a duck-typed stand-in with
+    the surface gen_grid_kernel / ApproxLMCLikelihood consume is used
+    (functional_kernel.py:225-300).
+Nothing from the reference is copied into this repository; only numbers.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse.linalg as sla
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, '..', '..'))
+sys.path.insert(0, '/root/reference')
+
+_orig_minres = sla.minres
+sla.minres = lambda A, b, tol=1e-5, **kw: _orig_minres(A, b, rtol=tol, **kw)
+
+from runlmc.linalg.toeplitz import Toeplitz  # noqa: E402
+from runlmc.linalg.bttb import BTTB  # noqa: E402
+from runlmc.linalg.kronecker import Kronecker  # noqa: E402
+from runlmc.linalg.numpy_matrix import NumpyMatrix  # noqa: E402
+from runlmc.linalg.sum_matrix import SumMatrix  # noqa: E402
+from runlmc.linalg.diag import Diag  # noqa: E402
+from runlmc.approx import interpolation as ref_interp  # noqa: E402
+from runlmc.approx.iterative import Iterative  # noqa: E402
+from runlmc.lmc.grid_kernel import gen_grid_kernel, GridKernel  # noqa: E402
+from runlmc.lmc.likelihood import ApproxLMCLikelihood  # noqa: E402
+from runlmc.lmc.stochastic_deriv import StochasticDerivService  # noqa: E402
+from runlmc.util.inline_pool import InlinePool  # noqa: E402
+
+from runlmc_b200 import synthetic  # noqa: E402
+
+
+class DuckKernel:
+    """Stand-in for FunctionalKernel; all kernels LMC-type (rank R_q +
+    diagonal), one active-dimension group."""
+
+    def __init__(self, prob):
+        self.p = prob
+        self.D, self.Q = prob.D, prob.Q
+        self.noise = prob.noise
+        self.coreg_vecs = prob.coreg_vecs
+        self.coreg_diags = prob.coreg_diags
+        self.ad = tuple(range(prob.ndim))
+        self.active_dims = {self.ad: list(range(prob.Q))}
+        self.num_lmc = {self.ad: prob.Q}
+        self.num_slfm = {self.ad: 0}
+        self.num_indep = {self.ad: 0}
+
+    def coreg_mats(self, active_dim=None):
+        return self.p.coreg_mats()
+
+    def total_rank(self, active_dim):
+        return sum(len(a) for a in self.coreg_vecs)
+
+    def eval_kernels(self, dists):
+        return [synthetic.rbf_top(dists[self.ad], g) for g in self.p.gammas]
+
+    def eval_kernels_fixed_dim(self, dists, active_dim):
+        return np.array([synthetic.rbf_top(dists, g) for g in self.p.gammas])
+
+    def eval_kernel_gradients(self, dists):
+        return [[synthetic.rbf_top_grad(dists[self.ad], g)]
+                for g in self.p.gammas]
+
+    def get_active_dims(self, q):
+        return self.ad
+
+    def filter_non_indep_idxs(self, idxs):
+        return list(idxs)
+
+
+def linalg_cases():
+    out = {}
+    rs = np.random.RandomState(7)
+    # Toeplitz tops: the deterministic ones of test_toeplitz.py:22-35 plus
+    # seeded exponential-decay tops (testing_utils.py:84-94)
+    tops = [
+        [1.], [1., 0.], [1., 1.], [0., 0.], [1., -1.],
+        [3.5] + [0.999] * 5 + [0.] * 110,
+        list((np.arange(10) + 1)[::-1].astype(float)),
+        list(np.exp(-rs.rand() * np.arange(10))),
+        list(np.exp(-rs.rand() * np.arange(50))),
+        list(np.exp(-rs.rand() * np.arange(100))),
+        list(np.exp(-0.01 * np.arange(300))),
+    ]
+    for i, t in enumerate(tops):
+        t = np.array(t)
+        x = np.arange(len(t)) + 1.0
+        out['toep_top_%d' % i] = t
+        out['toep_x_%d' % i] = x
+        out['toep_y_%d' % i] = Toeplitz(t).matvec(x)
+    out['toep_count'] = np.array(len(tops))
+    # BTTB shapes of test_bttb.py:17-27, arange and random tops, + larger 2-D
+    shapes = [(1,), (3,), (2, 3), (10,), (100,), (2, 3, 4), (5, 7), (16, 16),
+              (12, 40)]
+    k = 0
+    for sh in shapes:
+        for top in (np.arange(np.prod(sh)).astype(float),
+                    rs.rand(int(np.prod(sh)))):
+            x = rs.randn(int(np.prod(sh)))
+            out['bttb_shape_%d' % k] = np.array(sh)
+            out['bttb_top_%d' % k] = top
+            out['bttb_x_%d' % k] = x
+            out['bttb_y_%d' % k] = BTTB(top, sh).matvec(x)
+            k += 1
+    out['bttb_count'] = np.array(k)
+    # Kronecker(NumpyMatrix, Toeplitz/BTTB) and the SumMatrix(Kronecker...)+Diag
+    # shape of test_sum_matrix.py:57-58
+    A = rs.randn(3, 3)
+    A = A + A.T
+    t = np.exp(-0.3 * np.arange(10))
+    x = rs.randn(30)
+    out['kron_A'], out['kron_top'], out['kron_x'] = A, t, x
+    out['kron_y'] = Kronecker(NumpyMatrix(A), Toeplitz(t)).matvec(x)
+    mats, As, ts = [], [], []
+    for _ in range(5):
+        Aq = rs.randn(2, 2)
+        Aq = Aq + Aq.T
+        tq = np.exp(-rs.rand() * np.arange(5))
+        As.append(Aq)
+        ts.append(tq)
+        mats.append(Kronecker(NumpyMatrix(Aq), Toeplitz(tq)))
+    dg = np.ones(10) * 1e-4
+    mats.append(Diag(dg))
+    x = rs.randn(10)
+    out['sum_As'], out['sum_tops'], out['sum_diag'] = (
+        np.array(As), np.array(ts), dg)
+    out['sum_x'] = x
+    out['sum_y'] = SumMatrix(mats).matvec(x)
+    return out
+
+
+def interp_cases():
+    out = {}
+    rs = np.random.RandomState(11)
+    # test_interpolation.py:84-93
+    grid = np.arange(-0.1, 10.1, 0.1)
+    sample = np.arange(10) + 0.5
+    out['c1_grid'], out['c1_sample'] = grid, sample
+    out['c1_dense'] = ref_interp.interp_cubic(grid, sample).toarray()
+    # clamped / extrapolating samples (test_interpolation.py:66-82)
+    grid = np.arange(10.0)
+    sample = np.array([-2.5, -2., -1.2, -0.3, 0., 0.4, 1.7, 7.5, 8.2, 8.999,
+                       9., 9.6, 10.3, 11., 11.5])
+    out['c2_grid'], out['c2_sample'] = grid, sample
+    out['c2_dense'] = ref_interp.interp_cubic(grid, sample).toarray()
+    # random interior
+    grid = np.linspace(0, 1, 50)
+    sample = rs.uniform(0, 1, 200)
+    out['c3_grid'], out['c3_sample'] = grid, sample
+    out['c3_dense'] = ref_interp.interp_cubic(grid, sample).toarray()
+    # bicubic: interior, touching and outside the grid
+    gx = np.linspace(0, 1, 12)
+    gy = np.linspace(-1, 2, 9)
+    s2 = np.column_stack([rs.uniform(-0.3, 1.3, 150),
+                          rs.uniform(-1.8, 2.8, 150)])
+    s2[:5] = [[0, -1], [1, 2], [0.5, 0.5], [-0.2, 2.5], [1.2, -1.5]]
+    out['b1_gx'], out['b1_gy'], out['b1_sample'] = gx, gy, s2
+    out['b1_dense'] = ref_interp.interp_bicubic(gx, gy, s2).toarray()
+    # multi_interpolant 1-D and 2-D (test_interpolation.py:159-185)
+    grid = np.arange(-0.1, 10.1, 0.1)
+    sa, sb = np.arange(10) + 0.5, np.sin(np.arange(6)) + 4
+    out['m1_grid'], out['m1_sa'], out['m1_sb'] = grid, sa, sb
+    out['m1_dense'] = ref_interp.multi_interpolant([sa, sb], grid).toarray()
+    gx = np.arange(-0.1, 10.1, 0.5)
+    gy = np.arange(-2, 11, 0.5)
+    sa = np.column_stack([np.arange(10) + 0.5, np.ones(10)])
+    sb = np.column_stack([np.sin(np.arange(6)) + 4, np.arange(6.0)])
+    out['m2_gx'], out['m2_gy'], out['m2_sa'], out['m2_sb'] = gx, gy, sa, sb
+    out['m2_dense'] = ref_interp.multi_interpolant([sa, sb], gx, gy).toarray()
+    # autogrid (interpolation.py:179-215)
+    Xs = [np.arange(10.0).reshape(-1, 1), np.arange(4.0, 12).reshape(-1, 1)]
+    out['ag_a'] = ref_interp.autogrid(Xs, None, None, None)[0]
+    out['ag_b'] = ref_interp.autogrid(Xs, [-1], [13], [10])[0]
+    return out
+
+
+def lmc_case(prob, tol=1e-4, n_vec=3, reps=('sum', 'bt', 'slfm'),
+             grads=True, seed=5):
+    """Full path through the reference: gen_grid_kernel -> K.matvec,
+    Iterative.solve, ApproxLMCLikelihood gradients with recorded probes."""
+    out = {}
+    fk = DuckKernel(prob)
+    ad = fk.ad
+    W = ref_interp.multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    dists = {ad: prob.dists}
+    interps = {ad: (W, WT)}
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    rs = np.random.RandomState(seed)
+    V = rs.randn(n_vec, prob.n)
+    out['V'] = V
+    out['KV'] = np.array([K.matvec(v) for v in V])
+    # the three equivalent grid representations (grid_kernel.py:22-41)
+    for rep in reps:
+        gk = GridKernel(fk, prob.dists, W, WT, rep, ad)
+        out['KV_' + rep] = np.array([gk.matvec(v) for v in V])
+    out['WTV'] = np.array([WT.dot(v) for v in V])
+    G = rs.randn(n_vec, W.shape[1])
+    out['G'] = G
+    out['WG'] = np.array([W.dot(g) for g in G])
+    gk = GridKernel(fk, prob.dists, W, WT, 'sum', ad)
+    out['KUU_G'] = np.array([gk.grid_K.matvec(g) for g in G])
+    # solves
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, minres=True,
+                                  tol=tol)
+    out['solve_y_x'], out['solve_y_ctr'], out['solve_y_err'] = (
+        x, np.array(ctr), np.array(err))
+    if grads:
+        np.random.seed(seed)
+        svc = StochasticDerivService(None, InlinePool(None), prob.N, tol)
+        lik = ApproxLMCLikelihood(fk, K, dists, interps, prob.Ys, svc)
+        out['probes'] = np.array(lik.deriv._rs, dtype=np.float64)
+        out['inv_probes'] = np.array(lik.deriv._inv_rs)
+        out['alpha'] = lik.deriv.alpha
+        out['g_coreg_vec'] = np.array(lik.coreg_vec_gradients())
+        out['g_coreg_diag'] = np.array(lik.coreg_diags_gradients())
+        out['g_kernel'] = np.array(lik.kernel_gradients())
+        out['g_noise'] = lik.noise_gradient()
+    return out
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, 'linalg.npz'), **linalg_cases())
+    np.savez_compressed(os.path.join(HERE, 'interp.npz'), **interp_cases())
+    # config A (README scale), 1-D, edge-touching inputs
+    pa = synthetic.make_problem('A', seed=1234, edge=True,
+                                cells_per_lengthscale=4)
+    np.savez_compressed(os.path.join(HERE, 'lmc_A.npz'), **lmc_case(pa))
+    # small 2-D problem
+    pe = synthetic.make_problem('e_small', seed=99, cells_per_lengthscale=3,
+                                lens=[120, 90, 100], grid=[12, 10], N=5)
+    np.savez_compressed(os.path.join(HERE, 'lmc_2d.npz'), **lmc_case(pe))
+    # medium 1-D problem with the bench recipe's own gammas (ill-conditioned:
+    # scipy's test1 stop fires before the residual check)
+    pb = synthetic.make_problem('B', seed=1234, lens=[400, 380], grid=[128],
+                                N=4)
+    np.savez_compressed(os.path.join(HERE, 'lmc_B.npz'),
+                        **lmc_case(pb, reps=('sum',)))
+    print('golden vectors written to', HERE)
+
+
+if __name__ == '__main__':
+    main()
