@@ -1,0 +1,126 @@
+/* lmc_b200.h -- C ABI of the B200-native SKI-LMC hot path.
+ *
+ * The reference (vlad17/runlmc) is pure Python and has no FFI; the seam this
+ * library plugs into is the duck-typed operator protocol of runlmc/linalg
+ * (Matrix.matvec / matmat, matrix.py:43-67), Iterative.solve
+ * (approx/iterative.py:24) and StochasticDerivService/StochasticDeriv
+ * (lmc/stochastic_deriv.py:27-78).  Each entry point below names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success, 1 for an invalid argument, 2 for a
+ *    CUDA failure; lmc_last_error() gives the text.  Non-convergence of MINRES
+ *    is NOT an error (reference iterative.py:54-58 only logs).
+ *  - all floating point data is float64.  A block of P vectors of length n is
+ *    stored vector-major: V[p*ld + i] (ld >= n), i.e. each right-hand side is
+ *    contiguous, like the rows of the reference's probe matrix `rs`
+ *    (stochastic_deriv.py:35).
+ *  - pointers named *_dev are device pointers on the current CUDA device,
+ *    *_host are host pointers.  `stream` is a cudaStream_t passed as void*
+ *    (NULL = default stream).  Device entry points are stream-ordered and do not
+ *    synchronise unless stated.
+ *  - vectors of length n are in the caller's point order: outputs concatenated,
+ *    np.hstack(Ys) (reference lmc/likelihood.py:30).
+ */
+#ifndef LMC_B200_H
+#define LMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmc_op lmc_op;     /* fused SKI-LMC operator  K~ = W (sum_q B_q (x) T_q) W^T + diag(noise) */
+typedef struct lmc_bttb lmc_bttb; /* stand-alone symmetric (block-)Toeplitz operator */
+
+int lmc_version(void);
+const char* lmc_last_error(void);
+/* number of CUDA kernels launched by this library so far in this process */
+unsigned long long lmc_launch_count(void);
+
+/* ---- fused operator ------------------------------------------------------
+ * Replaces the operator tree built by gen_grid_kernel (lmc/grid_kernel.py:49-74):
+ * SumMatrix([GridKernel(SKI(sum|bt|slfm grid kernel, W, W^T)), Diag(noise)]).
+ * X_host: [n][ndim] coordinates, outputs concatenated; lens[D] points per output.
+ * The grid along axis p is origin[p] + k*delta[p], k < grid_sizes[p]
+ * (origin = grid[0], delta = grid[1]-grid[0], as interpolation.py:98).
+ * ndim is 1 or 2, D <= 16.  The X-dependent sort is done here, once.          */
+int lmc_op_create(lmc_op** out, int D, int ndim, const int* grid_sizes, const double* origin,
+                  const double* delta, const int* lens, const double* X_host);
+int lmc_op_destroy(lmc_op* op);
+/* Per-optimiser-step update.  tops_host [Q][prod grid_sizes]: kernel values
+ * k_q(|z - z_0|) on the grid (grid_kernel.py:26-27); B_host [Q][D][D]:
+ * coregionalisation matrices (functional_kernel.py:280-287); noise_host [D].    */
+int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* B_host,
+                      const double* noise_host);
+long lmc_op_n(const lmc_op* op);          /* total points */
+long lmc_op_grid_cells(const lmc_op* op); /* m = prod grid_sizes */
+long lmc_op_embed_bins(const lmc_op* op); /* prod of the power-of-two embedding sizes */
+/* sorted position -> caller index (int32[n]); the solver keeps its state in this order */
+int lmc_op_perm(const lmc_op* op, int* perm_host);
+
+/* OUT = K~ V  (SumMatrix.matvec, sum_matrix.py:31-32, over the whole tree)     */
+int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream);
+int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_host);
+/* unit-testable stages.  Grid vectors are [P][D*m], output-major (likelihood.py:30):
+ *   lmc_to_grid    G = W^T V      (WT.dot, ski.py:16)
+ *   lmc_grid_mvm   GOUT = (sum_q B_q (x) T_q) GIN   (grid_kernel.py:126-136)
+ *   lmc_from_grid  OUT = W G      (W.dot, ski.py:14)                           */
+int lmc_to_grid(lmc_op* op, const double* V_dev, long ld, int P, double* G_dev, void* stream);
+int lmc_grid_mvm(lmc_op* op, const double* GIN_dev, int P, double* GOUT_dev, void* stream);
+int lmc_from_grid(lmc_op* op, const double* G_dev, int P, double* OUT_dev, long ld, void* stream);
+
+/* ---- batched MINRES --------------------------------------------------------
+ * Replaces pool.starmap(Iterative.solve, [(K, rhs_p, True, True, tol)...])
+ * (stochastic_deriv.py:39-52): scipy's Paige-Saunders recurrence and stopping
+ * rules per column with rtol = min(1e-10, tol), maxiter (reference: n), plus the
+ * reference's true-residual test ||b - K x||_2 < tol on every `check_every`-th
+ * iteration (iterative.py:36-42, 100 in the reference).
+ * iters[P]  <- number of iterations (callback count) per column
+ * resid[P]  <- final ||b - K x||_2 per column (iterative.py:53)
+ * istop[P]  <- scipy istop code, or 10 if stopped by the residual test         */
+int lmc_minres(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol,
+               int maxiter, int check_every, int* iters_host, double* resid_host,
+               int* istop_host, void* stream);
+int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host,
+                    double tol, int maxiter, int check_every, int* iters_host,
+                    double* resid_host, int* istop_host);
+
+/* ---- gradient contractions -------------------------------------------------
+ * Everything StochasticDeriv.derivative (stochastic_deriv.py:69-78) needs for all
+ * hyper-parameters of ApproxLMCLikelihood (likelihood.py:48-96) at once.
+ * For each "top" t (the Q kernels first, then ntops_extra derivative tops
+ * d k_q / d theta, likelihood.py:121-124) returns the D x D Gram matrices
+ *   quad [t][d][e] = (W^T alpha)_d^T  T_t (W^T alpha)_e
+ *   trace[t][d][e] = sum_i (W^T Kinv r_i)_d^T T_t (W^T r_i)_e      (sum over N probes)
+ * and per output   nquad[d] = sum_{i in d} alpha_i^2,  ntrace[d] = sum_probes sum_{i in d} (Kinv r)_i r_i.
+ * dK for A_q[r,j], kappa_q[i], kernel parameters and noise are then
+ * <C, Gram> Frobenius products formed on the host (see runlmc_b200/lmc).       */
+int lmc_grad_grams(lmc_op* op, const double* alpha_dev, const double* R_dev, const double* RINV_dev,
+                   long ld, int N, int ntops_extra, const double* tops_extra_host,
+                   double* quad_host, double* trace_host, double* nquad_host, double* ntrace_host,
+                   void* stream);
+
+/* ---- stand-alone structured operators (runlmc/linalg mirror) ----------------
+ * lmc_bttb: BTTB(top, sizes).matvec (bttb.py:91-148), ndim <= 3; ndim == 1 also
+ * serves Toeplitz(top).matvec (toeplitz.py:34-67).  X/Y are [k][m] blocks.     */
+int lmc_bttb_create(lmc_bttb** out, int ndim, const int* sizes, const double* top_host);
+int lmc_bttb_destroy(lmc_bttb* h);
+int lmc_bttb_apply(lmc_bttb* h, const double* X_dev, int k, double* Y_dev, void* stream);
+/* Y[k][r][i] = sum_c A[r][c] X[k][c][i], small dense A on device (NumpyMatrix.matmat,
+ * numpy_matrix.py:30-31; inner > 1 is the A-side contraction of Kronecker.matvec, kronecker.py:39-46) */
+int lmc_dense_apply(const double* A_dev, int rows, int cols, const double* X_dev, int k, int inner,
+                    double* Y_dev, void* stream);
+/* Y[k][b][a] = X[k][a][b]  (the reshape/transposes of Kronecker.matvec, kronecker.py:41-44) */
+int lmc_transpose(const double* X_dev, int k, int a, int b, double* Y_dev, void* stream);
+/* Y[k][rows] = CSR(rows x cols) * X[k][cols]   (scipy CSR .dot used by SKI, ski.py:14-16) */
+int lmc_csr_apply(int rows, const int* indptr_dev, const int* indices_dev, const double* data_dev,
+                  const double* X_dev, long ldx, int k, double* Y_dev, long ldy, void* stream);
+/* Y = a*X + b*Y elementwise over len entries (SumMatrix accumulation) */
+int lmc_axpby(long len, double a, const double* X_dev, double b, double* Y_dev, void* stream);
+/* Y[k][len] = v[len] * X[k][len]  (Diag.matmat, diag.py:27-28) */
+int lmc_diag_apply(const double* v_dev, long len, const double* X_dev, int k, double* Y_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMC_B200_H */

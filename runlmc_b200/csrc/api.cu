@@ -1,0 +1,199 @@
+// C ABI of the fused SKI-LMC operator (include/lmc_b200.h).
+#include "../../include/lmc_b200.h"
+#include "op.cuh"
+
+#include <vector>
+
+using namespace lmc;
+
+namespace {
+struct HostBlock {  // device staging for the *_host entry points
+    double* p = nullptr;
+    ~HostBlock() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" {
+
+int lmc_version(void) { return 100; }
+const char* lmc_last_error(void) { return get_error(); }
+unsigned long long lmc_launch_count(void) { return g_launches; }
+
+int lmc_op_create(lmc_op** out, int D, int ndim, const int* grid_sizes, const double* origin,
+                  const double* delta, const int* lens, const double* X_host) {
+    LMC_REQUIRE(out && grid_sizes && origin && delta && lens && X_host, "null argument");
+    LMC_REQUIRE(ndim == 1 || ndim == 2, "ndim must be 1 or 2");
+    lmc_op* op = new lmc_op();
+    op->D = D;
+    op->ndim = ndim;
+    int rc = embedding_init(&op->emb, ndim, grid_sizes);
+    if (rc == 0) rc = op->eng.init(op->emb);
+    if (rc == 0) rc = build_points(&op->ps, D, ndim, grid_sizes, origin, delta, lens, X_host, op->emb.grid_pitch);
+    if (rc != 0) { delete op; return rc; }
+    *out = op;
+    return 0;
+}
+
+int lmc_op_destroy(lmc_op* op) {
+    delete op;
+    return 0;
+}
+
+int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* B_host,
+                      const double* noise_host) {
+    LMC_REQUIRE(op && tops_host && B_host && noise_host, "null argument");
+    LMC_REQUIRE(Q >= 1 && Q <= 64, "Q must be in 1..64");
+    const long bins = op->emb.bins, cells = op->emb.cells;
+    const int D = op->D;
+    if (Q > op->spec_cap) {
+        cudaFree(op->spec); cudaFree(op->B);
+        op->spec = nullptr; op->B = nullptr; op->spec_cap = 0;
+        LMC_CHECK(cudaMalloc(&op->spec, sizeof(double) * (size_t)Q * bins));
+        LMC_CHECK(cudaMalloc(&op->B, sizeof(double) * (size_t)Q * D * D));
+        op->spec_cap = Q;
+    }
+    if (!op->noise) LMC_CHECK(cudaMalloc(&op->noise, sizeof(double) * D));
+    double* top_dev = nullptr;
+    cplx* work = nullptr;
+    LMC_CHECK(cudaMalloc(&top_dev, sizeof(double) * (size_t)Q * cells));
+    cudaError_t e = cudaMalloc(&work, sizeof(cplx) * (size_t)bins);
+    if (e != cudaSuccess) { cudaFree(top_dev); LMC_CHECK(e); }
+    int rc = 0;
+    e = cudaMemcpy(top_dev, tops_host, sizeof(double) * (size_t)Q * cells, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(op->B, B_host, sizeof(double) * (size_t)Q * D * D, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(op->noise, noise_host, sizeof(double) * D, cudaMemcpyHostToDevice);
+    for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q)
+        rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
+    if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
+    cudaFree(top_dev);
+    cudaFree(work);
+    if (rc != 0) return rc;
+    LMC_CHECK(e);
+    op->Q = Q;
+    return 0;
+}
+
+long lmc_op_n(const lmc_op* op) { return op ? op->ps.n : -1; }
+long lmc_op_grid_cells(const lmc_op* op) { return op ? op->emb.cells : -1; }
+long lmc_op_embed_bins(const lmc_op* op) { return op ? op->emb.bins : -1; }
+
+int lmc_op_perm(const lmc_op* op, int* perm_host) {
+    LMC_REQUIRE(op && perm_host, "null argument");
+    LMC_CHECK(cudaMemcpy(perm_host, op->ps.perm, sizeof(int) * op->ps.n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream) {
+    LMC_REQUIRE(op && V_dev && OUT_dev, "null argument");
+    LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    LMC_REQUIRE(V_dev != OUT_dev, "in-place product not supported");
+    ColumnView cv;
+    cv.in = V_dev; cv.out = OUT_dev; cv.ld = ld; cv.ncols = P;
+    return op_mvm(op, cv, (cudaStream_t)stream);
+}
+
+int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_host) {
+    LMC_REQUIRE(op && V_host && OUT_host, "null argument");
+    LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    if (P == 0) return 0;
+    HostBlock in, out;
+    const size_t bytes = sizeof(double) * (size_t)P * ld;
+    LMC_CHECK(cudaMalloc(&in.p, bytes));
+    LMC_CHECK(cudaMalloc(&out.p, bytes));
+    LMC_CHECK(cudaMemcpy(in.p, V_host, bytes, cudaMemcpyHostToDevice));
+    LMC_TRY(lmc_mvm(op, in.p, ld, P, out.p, nullptr));
+    LMC_CHECK(cudaMemcpy(OUT_host, out.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lmc_to_grid(lmc_op* op, const double* V_dev, long ld, int P, double* G_dev, void* stream) {
+    LMC_REQUIRE(op && V_dev && G_dev, "null argument");
+    LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    LMC_TRY(op_ensure_workspace(op));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npairs = (P + 1) / 2;
+    const long gm = (long)op->D * op->emb.cells;
+    for (int p0 = 0; p0 < npairs; p0 += op->tile_pairs) {
+        const int cnt = std::min(op->tile_pairs, npairs - p0);
+        ColumnView cv;
+        cv.in = V_dev + (long)2 * p0 * ld; cv.ld = ld; cv.ncols = std::min(2 * cnt, P - 2 * p0);
+        LMC_TRY(to_grid(op->ps, cv, op->G, st));
+        LMC_TRY(unpack_pairs(op->G, op->emb.grid_pitch, G_dev + (long)2 * p0 * gm, cv.ncols, op->D,
+                             op->emb.cells, st));
+    }
+    return 0;
+}
+
+int lmc_grid_mvm(lmc_op* op, const double* GIN_dev, int P, double* GOUT_dev, void* stream) {
+    LMC_REQUIRE(op && GIN_dev && GOUT_dev, "null argument");
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+    LMC_TRY(op_ensure_workspace(op));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npairs = (P + 1) / 2;
+    const long gm = (long)op->D * op->emb.cells;
+    for (int p0 = 0; p0 < npairs; p0 += op->tile_pairs) {
+        const int cnt = std::min(op->tile_pairs, npairs - p0);
+        const int ncols = std::min(2 * cnt, P - 2 * p0);
+        LMC_TRY(pack_pairs(GIN_dev + (long)2 * p0 * gm, ncols, op->D, op->emb.cells, op->G,
+                           op->emb.grid_pitch, st));
+        LMC_TRY(op_grid_apply(op, op->G, cnt, op->Q, op->spec, op->B, st));
+        LMC_TRY(unpack_pairs(op->G, op->emb.grid_pitch, GOUT_dev + (long)2 * p0 * gm, ncols, op->D,
+                             op->emb.cells, st));
+    }
+    return 0;
+}
+
+int lmc_from_grid(lmc_op* op, const double* G_dev, int P, double* OUT_dev, long ld, void* stream) {
+    LMC_REQUIRE(op && G_dev && OUT_dev, "null argument");
+    LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    LMC_TRY(op_ensure_workspace(op));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npairs = (P + 1) / 2;
+    const long gm = (long)op->D * op->emb.cells;
+    for (int p0 = 0; p0 < npairs; p0 += op->tile_pairs) {
+        const int cnt = std::min(op->tile_pairs, npairs - p0);
+        const int ncols = std::min(2 * cnt, P - 2 * p0);
+        LMC_TRY(pack_pairs(G_dev + (long)2 * p0 * gm, ncols, op->D, op->emb.cells, op->G,
+                           op->emb.grid_pitch, st));
+        ColumnView cv;
+        cv.out = OUT_dev + (long)2 * p0 * ld; cv.ld = ld; cv.ncols = ncols;
+        LMC_TRY(from_grid(op->ps, cv, op->G, nullptr, st));
+    }
+    return 0;
+}
+
+int lmc_minres(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol,
+               int maxiter, int check_every, int* iters_host, double* resid_host, int* istop_host,
+               void* stream) {
+    LMC_REQUIRE(op && RHS_dev && X_dev, "null argument");
+    return minres_solve(op, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+                        istop_host, (cudaStream_t)stream);
+}
+
+int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host, double tol,
+                    int maxiter, int check_every, int* iters_host, double* resid_host, int* istop_host) {
+    LMC_REQUIRE(op && RHS_host && X_host, "null argument");
+    LMC_REQUIRE(P >= 1 && ld >= op->ps.n, "bad block shape");
+    HostBlock in, out;
+    const size_t bytes = sizeof(double) * (size_t)P * ld;
+    LMC_CHECK(cudaMalloc(&in.p, bytes));
+    LMC_CHECK(cudaMalloc(&out.p, bytes));
+    LMC_CHECK(cudaMemcpy(in.p, RHS_host, bytes, cudaMemcpyHostToDevice));
+    LMC_CHECK(cudaMemset(out.p, 0, bytes));
+    LMC_TRY(minres_solve(op, in.p, ld, P, out.p, tol, maxiter, check_every, iters_host, resid_host,
+                         istop_host, nullptr));
+    LMC_CHECK(cudaMemcpy(X_host, out.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lmc_grad_grams(lmc_op* op, const double* alpha_dev, const double* R_dev, const double* RINV_dev,
+                   long ld, int N, int ntops_extra, const double* tops_extra_host, double* quad_host,
+                   double* trace_host, double* nquad_host, double* ntrace_host, void* stream) {
+    LMC_REQUIRE(op && alpha_dev && quad_host && trace_host && nquad_host && ntrace_host, "null argument");
+    LMC_REQUIRE(N == 0 || (R_dev && RINV_dev), "null probe blocks");
+    LMC_REQUIRE(ntops_extra == 0 || tops_extra_host, "null derivative tops");
+    return grad_grams(op, alpha_dev, R_dev, RINV_dev, ld, N, ntops_extra, tops_extra_host, quad_host,
+                      trace_host, nquad_host, ntrace_host, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Small device kernels backing the stand-alone runlmc.linalg mirror classes
+// (NumpyMatrix, Diag, SumMatrix accumulation, scipy-CSR products inside SKI).
+#include "op.cuh"
+
+namespace lmc {
+
+// Y[k][r][i] = sum_c A[r][c] X[k][c][i]   (NumpyMatrix.matmat = A.dot(X), numpy_matrix.py:30-31;
+// inner > 1 contracts the slow axis of a Kronecker reshape, kronecker.py:39-46)
+__global__ void dense_apply_kernel(const double* __restrict__ A, int rows, int cols,
+                                   const double* __restrict__ X, int k, int inner, double* Y) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)k * rows * inner) return;
+    const int i = (int)(idx % inner);
+    const long t = idx / inner;
+    const int r = (int)(t % rows);
+    const long v = t / rows;
+    const double* a = A + (long)r * cols;
+    const double* x = X + v * cols * inner + i;
+    double acc = 0.0;
+    for (int c = 0; c < cols; ++c) acc = fma(a[c], x[(long)c * inner], acc);
+    Y[idx] = acc;
+}
+
+// Y[k][b][a] = X[k][a][b]
+__global__ void transpose_kernel(const double* __restrict__ X, int k, int A, int B, double* Y) {
+    __shared__ double tile[32][33];
+    const int v = blockIdx.z;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    const double* x = X + (long)v * A * B;
+    double* y = Y + (long)v * A * B;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int a = a0 + j, b = b0 + threadIdx.x;
+        if (a < A && b < B) tile[j][threadIdx.x] = x[(long)a * B + b];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int b = b0 + j, a = a0 + threadIdx.x;
+        if (a < A && b < B) y[(long)b * A + a] = tile[threadIdx.x][j];
+    }
+}
+
+// Y[v][r] = sum_j data[j] X[v][indices[j]], j in [indptr[r], indptr[r+1])   (scipy CSR dot, ski.py:14-16)
+__global__ void csr_apply_kernel(int rows, const int* __restrict__ indptr, const int* __restrict__ indices,
+                                 const double* __restrict__ data, const double* __restrict__ X, long ldx,
+                                 int k, double* Y, long ldy) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)k * rows) return;
+    const int r = (int)(idx % rows);
+    const long v = idx / rows;
+    const double* x = X + v * ldx;
+    double acc = 0.0;
+    for (int j = indptr[r]; j < indptr[r + 1]; ++j) acc = fma(data[j], x[indices[j]], acc);
+    Y[v * ldy + r] = acc;
+}
+
+__global__ void axpby_kernel(long len, double a, const double* __restrict__ X, double b, double* Y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) Y[i] = (b == 0.0) ? a * X[i] : fma(a, X[i], b * Y[i]);
+}
+
+__global__ void diag_apply_kernel(const double* __restrict__ v, long len, const double* __restrict__ X, int k,
+                                  double* Y) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len * k) Y[i] = X[i] * v[i % len];
+}
+
+}  // namespace lmc
+
+using namespace lmc;
+
+extern "C" {
+
+int lmc_dense_apply(const double* A_dev, int rows, int cols, const double* X_dev, int k, int inner,
+                    double* Y_dev, void* stream) {
+    LMC_REQUIRE(rows >= 1 && cols >= 1 && k >= 0 && inner >= 1, "bad dense shape");
+    if (k == 0) return 0;
+    const long total = (long)k * rows * inner;
+    dense_apply_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(A_dev, rows, cols, X_dev, k,
+                                                                              inner, Y_dev);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int lmc_transpose(const double* X_dev, int k, int a, int b, double* Y_dev, void* stream) {
+    LMC_REQUIRE(k >= 0 && a >= 1 && b >= 1 && k < 65536, "bad transpose shape");
+    if (k == 0) return 0;
+    dim3 grid((unsigned)ceil_div(b, 32), (unsigned)ceil_div(a, 32), (unsigned)k);
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(X_dev, k, a, b, Y_dev);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int lmc_csr_apply(int rows, const int* indptr_dev, const int* indices_dev, const double* data_dev,
+                  const double* X_dev, long ldx, int k, double* Y_dev, long ldy, void* stream) {
+    LMC_REQUIRE(rows >= 0 && k >= 0, "bad csr shape");
+    const long total = (long)k * rows;
+    if (total == 0) return 0;
+    csr_apply_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(rows, indptr_dev, indices_dev,
+                                                                            data_dev, X_dev, ldx, k, Y_dev, ldy);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int lmc_axpby(long len, double a, const double* X_dev, double b, double* Y_dev, void* stream) {
+    if (len <= 0) return 0;
+    axpby_kernel<<<ceil_div(len, 256), 256, 0, (cudaStream_t)stream>>>(len, a, X_dev, b, Y_dev);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int lmc_diag_apply(const double* v_dev, long len, const double* X_dev, int k, double* Y_dev, void* stream) {
+    if (len <= 0 || k <= 0) return 0;
+    diag_apply_kernel<<<ceil_div(len * k, 256), 256, 0, (cudaStream_t)stream>>>(v_dev, len, X_dev, k, Y_dev);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---- stand-alone BTTB / Toeplitz ------------------------------------------
+int lmc_bttb_create(lmc_bttb** out, int ndim, const int* sizes, const double* top_host) {
+    LMC_REQUIRE(out && sizes && top_host, "null argument");
+    lmc_bttb* h = new lmc_bttb();
+    int rc = embedding_init(&h->emb, ndim, sizes);
+    if (rc == 0) rc = h->eng.init(h->emb);
+    if (rc != 0) { delete h; return rc; }
+    const long cells = h->emb.cells, bins = h->emb.bins;
+    double* top_dev = nullptr;
+    cplx* work = nullptr;
+    const double one = 1.0;
+    cudaError_t e = cudaMalloc(&top_dev, sizeof(double) * cells);
+    if (e == cudaSuccess) e = cudaMalloc(&work, sizeof(cplx) * bins);
+    if (e == cudaSuccess) e = cudaMalloc(&h->spec, sizeof(double) * bins);
+    if (e == cudaSuccess) e = cudaMalloc(&h->one, sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(top_dev, top_host, sizeof(double) * cells, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->one, &one, sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = h->eng.spectrum(top_dev, h->spec, work, 0);
+        if (rc == 0) e = cudaDeviceSynchronize();
+    }
+    cudaFree(top_dev);
+    cudaFree(work);
+    if (e != cudaSuccess || rc != 0) {
+        if (e != cudaSuccess) set_error(std::string("lmc_bttb_create: ") + cudaGetErrorString(e));
+        delete h;
+        return rc ? rc : 2;
+    }
+    *out = h;
+    return 0;
+}
+
+int lmc_bttb_destroy(lmc_bttb* h) {
+    delete h;
+    return 0;
+}
+
+int lmc_bttb_apply(lmc_bttb* h, const double* X_dev, int k, double* Y_dev, void* stream) {
+    LMC_REQUIRE(h && k >= 0, "bad argument");
+    if (k == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npairs = (k + 1) / 2;
+    if (npairs > h->cap_pairs) {
+        cudaFree(h->G);
+        cudaFree(h->S);
+        h->G = nullptr; h->S = nullptr; h->cap_pairs = 0;
+        const size_t gb = sizeof(cplx) * (size_t)npairs * h->emb.grid_pitch;
+        LMC_CHECK(cudaMalloc(&h->G, gb));
+        LMC_CHECK(cudaMemset(h->G, 0, gb));
+        LMC_CHECK(cudaMalloc(&h->S, sizeof(cplx) * (size_t)npairs * h->emb.bins));
+        h->cap_pairs = npairs;
+    }
+    LMC_TRY(pack_pairs(X_dev, k, 1, h->emb.cells, h->G, h->emb.grid_pitch, st));
+    LMC_TRY(h->eng.forward(h->G, h->S, npairs, st));
+    LMC_TRY(h->eng.mix(h->S, npairs, 1, 1, h->spec, h->one, st));
+    LMC_TRY(h->eng.inverse(h->S, h->G, npairs, st));
+    LMC_TRY(unpack_pairs(h->G, h->emb.grid_pitch, Y_dev, k, 1, h->emb.cells, st));
+    return 0;
+}
+
+}  // extern "C"

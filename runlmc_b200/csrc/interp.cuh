@@ -1,0 +1,47 @@
+// Cubic-convolution interpolation between scattered points and the inducing grid.
+#pragma once
+#include "common.cuh"
+
+namespace lmc {
+
+// Device-resident description of the (fixed) inputs X, sorted by
+// (output, grid bin).  Built once per operator by build_points() on the host.
+struct PointSet {
+    int D = 0, ndim = 0;
+    long n = 0;
+    int m[2] = {1, 1};    // grid sizes
+    int nb[2] = {1, 1};   // bins per axis = m + 3  (clamped base index i0 in [-2, m])
+    long NB = 0;          // bins per output
+    long grid_pitch = 0;  // cells allocated per (pair, output) slab
+    bool identity = false;  // sorted order == caller's order
+    int* perm = nullptr;     // [n] sorted position -> caller's index
+    double* u[2] = {nullptr, nullptr};  // [n] fractional offsets (sorted order)
+    int* i0[2] = {nullptr, nullptr};    // [n] clamped base index (sorted order)
+    int* bin_start = nullptr;           // [D*NB + 1] offsets into the sorted arrays
+    long out_start[17] = {0};           // host copy, [D+1] point offsets per output
+    long* out_start_dev = nullptr;
+};
+
+// Host-side build (counting sort by bin); reproduces f=(s-g0)/delta, i0=floor(f),
+// u=f-i0 of reference approx/interpolation.py:98-101 bit for bit.
+int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const double* origin,
+                 const double* delta, const int* lens, const double* X_host, long grid_pitch);
+void free_points(PointSet* ps);
+
+struct ColumnView {
+    const double* in = nullptr;  // [ncols][ld] input vectors (caller's order unless sorted_io)
+    double* out = nullptr;       // [ncols][ld] outputs
+    long ld = 0;
+    int ncols = 0;
+    const double* in_scale = nullptr;  // optional per-column factor applied to `in`
+    const int* active = nullptr;       // optional per-column flag; pairs with no active column are skipped
+    bool sorted_io = false;            // vectors already in the operator's sorted order
+};
+
+// G[pair][d][cell] (complex pairs of columns 2p, 2p+1)  <-  W^T in     (deterministic, no atomics)
+int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st);
+// out = W G (+ noise_d * in when noise != nullptr)
+int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const double* noise,
+              cudaStream_t st);
+
+}  // namespace lmc

@@ -1,0 +1,397 @@
+// Multi-right-hand-side MINRES on the fused SKI-LMC operator.
+//
+// Replaces pool.starmap(Iterative.solve, ...) of the reference
+// (runlmc/lmc/stochastic_deriv.py:39-52 -> runlmc/approx/iterative.py:24-62 ->
+// scipy.sparse.linalg.minres, scipy 1.18.1 _isolve/minres.py:210-364).
+// Every column runs scipy's Paige-Saunders recurrence with scipy's stopping
+// rules (rtol = min(1e-10, tol)) and the reference wrapper's true-residual test
+// every `check_every` iterations; columns stop independently (frozen once
+// stopped) while the block advances in lock step.
+//
+// State lives in the operator's sorted point order, vector-major [P][n]; the
+// Lanczos vector v is never materialised (v = r2 / beta is applied as a column
+// scale when r2 is read).  r1/r2/y and w1/w2/w rotate by pointer.  Dot products
+// are two-stage (per-CTA partials, fixed-order final sum) => deterministic.
+#include "op.cuh"
+
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+namespace lmc {
+
+struct ColState {
+    double beta1, beta, oldb, dbar, epsln, phibar, rhs1, rhs2, tnorm2, gmax, gmin, cs, sn;
+    double alfa, root;
+    double c_r1;                                   // beta / oldb for the next Lanczos step
+    double oldeps, delta, denom, phi, inv_oldb;    // coefficients of the w / x update
+    double resid;
+    int istop, itn, done;
+};
+
+static const int kVecThreads = 256;
+static const int kVecPerThread = 8;
+static const int kVecChunk = kVecThreads * kVecPerThread;
+
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double s_red[32];
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? s_red[threadIdx.x] : 0.0;
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    if (threadIdx.x == 0) s_red[0] = v;
+    __syncthreads();
+    return s_red[0];
+}
+
+// fixed-order sum of `cnt` partials by the whole block (same value in every CTA)
+__device__ __forceinline__ double block_sum_partials(const double* part, int cnt) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += part[i];
+    return block_reduce_sum(v);
+}
+
+// b_sorted[c][i] = RHS[c][perm[i]];  r2 = b; x = w = w1 = w2 = 0; partial ||b||^2
+__global__ void __launch_bounds__(kVecThreads) minres_init_kernel(
+    const double* __restrict__ RHS, long ld, const int* __restrict__ perm, long n, double* b,
+    double* r2, double* x, double* w, double* w1, double* w2, double* part, int nblk) {
+    const int col = blockIdx.y;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const double v = RHS[(long)col * ld + (perm ? perm[i] : i)];
+            const long o = (long)col * n + i;
+            b[o] = v; r2[o] = v; x[o] = 0.0; w[o] = 0.0; w1[o] = 0.0; w2[o] = 0.0;
+            acc = fma(v, v, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+__global__ void minres_init_scalars_kernel(ColState* st, double* inv_beta, int* active, const double* part,
+                                           int nblk, int P, int* n_active) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < P) {
+        double s = 0.0;
+        for (int i = 0; i < nblk; ++i) s += part[(long)col * nblk + i];
+        ColState c = {};
+        c.beta1 = sqrt(s);
+        c.beta = c.beta1; c.oldb = 0.0; c.dbar = 0.0; c.epsln = 0.0; c.phibar = c.beta1;
+        c.rhs1 = c.beta1; c.rhs2 = 0.0; c.tnorm2 = 0.0; c.gmax = 0.0; c.gmin = DBL_MAX;
+        c.cs = -1.0; c.sn = 0.0; c.c_r1 = 0.0; c.istop = 0; c.itn = 0;
+        c.done = (c.beta1 == 0.0) ? 1 : 0;  // scipy returns x = 0 at once
+        st[col] = c;
+        inv_beta[col] = c.done ? 0.0 : 1.0 / c.beta1;
+        active[col] = c.done ? 0 : 1;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_active = -1;  // recomputed by the first status kernel
+}
+
+// y -= (beta/oldb) r1 ; alfa partial = sum (r2/beta) * y
+__global__ void __launch_bounds__(kVecThreads) minres_k1_kernel(
+    double* y, const double* __restrict__ r1, const double* __restrict__ r2, const ColState* st,
+    const double* inv_beta, const int* active, long n, double* part, int nblk) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const double c = st[col].c_r1, s = inv_beta[col];
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            double yv = y[o];
+            if (c != 0.0) yv = __dsub_rn(yv, __dmul_rn(c, r1[o]));
+            y[o] = yv;
+            acc = fma(__dmul_rn(s, r2[o]), yv, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// alfa = sum partials ; y -= (alfa/beta) r2 ; beta^2 partial = sum y^2
+__global__ void __launch_bounds__(kVecThreads) minres_k2_kernel(
+    double* y, const double* __restrict__ r2, ColState* st, const int* active, long n,
+    const double* part_a, double* part_b, int nblk) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const double alfa = block_sum_partials(part_a + (long)col * nblk, nblk);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[col].alfa = alfa;
+    const double c = alfa / st[col].beta;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            const double yv = __dsub_rn(y[o], __dmul_rn(c, r2[o]));
+            y[o] = yv;
+            acc = fma(yv, yv, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part_b[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// scalar recurrences after the Lanczos step (minres.py:236-283)
+__global__ void minres_s1_kernel(ColState* st, const int* active, const double* part_b, int nblk, int P) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= P || !active[col]) return;
+    ColState c = st[col];
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += part_b[(long)col * nblk + i];
+    c.itn += 1;
+    c.oldb = c.beta;
+    c.beta = sqrt(s);
+    c.tnorm2 += c.alfa * c.alfa + c.oldb * c.oldb + c.beta * c.beta;
+    if (c.itn == 1 && c.beta / c.beta1 <= 10 * DBL_EPSILON) c.istop = -1;
+    c.oldeps = c.epsln;
+    c.delta = c.cs * c.dbar + c.sn * c.alfa;
+    const double gbar = c.sn * c.dbar - c.cs * c.alfa;
+    c.epsln = c.sn * c.beta;
+    c.dbar = -c.cs * c.beta;
+    c.root = sqrt(gbar * gbar + c.dbar * c.dbar);
+    double gamma = sqrt(gbar * gbar + c.beta * c.beta);
+    gamma = fmax(gamma, DBL_EPSILON);
+    c.cs = gbar / gamma;
+    c.sn = c.beta / gamma;
+    c.phi = c.cs * c.phibar;
+    c.phibar = c.sn * c.phibar;
+    c.denom = 1.0 / gamma;
+    c.inv_oldb = 1.0 / c.oldb;
+    c.gmax = fmax(c.gmax, gamma);
+    c.gmin = fmin(c.gmin, gamma);
+    const double z = c.rhs1 / gamma;
+    c.rhs1 = c.rhs2 - c.delta * z;
+    c.rhs2 = -c.epsln * z;
+    st[col] = c;
+}
+
+// scipy: w1 = w2; w2 = w; w = (v - oldeps*w1 - delta*w2)*denom, i.e. with the two most
+// recent directions w_older (= old w2) and w_newer (= old w):
+//   w_out = (v - oldeps w_older - delta w_newer) * denom ; x += phi w_out ; ||x||^2 partial
+__global__ void __launch_bounds__(kVecThreads) minres_k3_kernel(
+    double* __restrict__ w_out, const double* __restrict__ w_older, const double* __restrict__ w_newer,
+    const double* __restrict__ vsrc, double* x, const ColState* st, const int* active, long n,
+    double* part, int nblk) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const ColState* c = st + col;
+    const double oldeps = c->oldeps, delta = c->delta, denom = c->denom, phi = c->phi, s = c->inv_oldb;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            const double v = __dmul_rn(s, vsrc[o]);
+            double t = __dsub_rn(v, __dmul_rn(oldeps, w_older[o]));
+            t = __dsub_rn(t, __dmul_rn(delta, w_newer[o]));
+            const double wn = __dmul_rn(t, denom);
+            w_out[o] = wn;
+            const double xv = __dadd_rn(x[o], __dmul_rn(phi, wn));
+            x[o] = xv;
+            acc = fma(xv, xv, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// norms + stopping rules (minres.py:285-330); prepares the next step's scales
+__global__ void minres_s2_kernel(ColState* st, double* inv_beta, int* active, const double* part_c, int nblk,
+                                 int P, double rtol, int maxiter, int* n_active) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int col = threadIdx.x; col < P; col += blockDim.x) {
+        if (active[col]) {
+            ColState c = st[col];
+            double s = 0.0;
+            for (int i = 0; i < nblk; ++i) s += part_c[(long)col * nblk + i];
+            const double ynorm = sqrt(s);
+            const double Anorm = sqrt(c.tnorm2);
+            const double epsx = Anorm * ynorm * DBL_EPSILON;
+            const double rnorm = c.phibar;
+            const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
+            const double test2 = (Anorm == 0.0) ? INFINITY : c.root / Anorm;
+            const double Acond = c.gmax / c.gmin;
+            if (c.istop == 0) {
+                if (1.0 + test2 <= 1.0) c.istop = 2;
+                if (1.0 + test1 <= 1.0) c.istop = 1;
+                if (c.itn >= maxiter) c.istop = 6;
+                if (Acond >= 0.1 / DBL_EPSILON) c.istop = 4;
+                if (epsx >= c.beta1) c.istop = 3;
+                if (test2 <= rtol) c.istop = 2;
+                if (test1 <= rtol) c.istop = 1;
+            }
+            c.c_r1 = c.beta / c.oldb;
+            if (c.istop != 0) { c.done = 1; active[col] = 0; }
+            else { inv_beta[col] = 1.0 / c.beta; atomicAdd(&s_cnt, 1); }
+            st[col] = c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_active = s_cnt;
+}
+
+// partial ||b - y||^2
+__global__ void __launch_bounds__(kVecThreads) minres_resid_kernel(
+    const double* __restrict__ b, const double* __restrict__ y, const int* active, long n, double* part,
+    int nblk) {
+    const int col = blockIdx.y;
+    if (active && !active[col]) return;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            const double dlt = __dsub_rn(b[o], y[o]);
+            acc = fma(dlt, dlt, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// reference early termination (iterative.py:36-42): residual < tol stops the column
+__global__ void minres_s3_kernel(ColState* st, int* active, const double* part, int nblk, int P, double tol,
+                                 int final_pass, int* n_active) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int col = threadIdx.x; col < P; col += blockDim.x) {
+        if (final_pass || active[col]) {
+            double s = 0.0;
+            for (int i = 0; i < nblk; ++i) s += part[(long)col * nblk + i];
+            const double r = sqrt(s);
+            st[col].resid = r;
+            if (!final_pass) {
+                if (r < tol) { st[col].istop = 10; st[col].done = 1; active[col] = 0; }
+                else atomicAdd(&s_cnt, 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !final_pass) *n_active = s_cnt;
+}
+
+__global__ void __launch_bounds__(kVecThreads) minres_finish_kernel(
+    const double* __restrict__ x, const int* __restrict__ perm, long n, double* X, long ld) {
+    const int col = blockIdx.y;
+    const long base = (long)blockIdx.x * kVecChunk;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) X[(long)col * ld + (perm ? perm[i] : i)] = x[(long)col * n + i];
+    }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { LMC_CHECK(cudaMalloc(&p, bytes ? bytes : 8)); return 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st) {
+    LMC_REQUIRE(P >= 1, "need at least one right-hand side");
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+    LMC_REQUIRE(maxiter >= 1 && check_every >= 1, "maxiter/check_every must be positive");
+    const long n = op->ps.n;
+    LMC_REQUIRE(ld >= n, "leading dimension < n");
+    const int nblk = ceil_div(n, kVecChunk);
+    const double rtol = std::fmin(1e-10, tol);
+    const size_t vec = sizeof(double) * (size_t)P * n;
+    DevBuf bufs[8], parts[3], stb, invb, act, nact;
+    for (auto& b : bufs) LMC_TRY(b.alloc(vec));
+    for (auto& b : parts) LMC_TRY(b.alloc(sizeof(double) * (size_t)P * nblk));
+    LMC_TRY(stb.alloc(sizeof(ColState) * P));
+    LMC_TRY(invb.alloc(sizeof(double) * P));
+    LMC_TRY(act.alloc(sizeof(int) * P));
+    LMC_TRY(nact.alloc(sizeof(int)));
+    double *b = bufs[0].as<double>(), *x = bufs[1].as<double>();
+    double *r1 = bufs[2].as<double>(), *r2 = bufs[3].as<double>(), *y = bufs[4].as<double>();
+    // wa = older direction (scipy's w2), wb = newer (scipy's w), wc = free buffer
+    double *wa = bufs[5].as<double>(), *wb = bufs[6].as<double>(), *wc = bufs[7].as<double>();
+    double *pa = parts[0].as<double>(), *pb = parts[1].as<double>(), *pc = parts[2].as<double>();
+    ColState* cs = stb.as<ColState>();
+    double* inv_beta = invb.as<double>();
+    int* active = act.as<int>();
+    int* n_active = nact.as<int>();
+    const int* perm = op->ps.identity ? nullptr : op->ps.perm;
+    const dim3 vgrid((unsigned)nblk, (unsigned)P);
+    const int sthreads = 128, sblocks = ceil_div(P, sthreads);
+
+    minres_init_kernel<<<vgrid, kVecThreads, 0, st>>>(RHS, ld, perm, n, b, r2, x, wa, wb, wc, pa, nblk);
+    minres_init_scalars_kernel<<<sblocks, sthreads, 0, st>>>(cs, inv_beta, active, pa, nblk, P, n_active);
+    count_launch(2);
+    LMC_CHECK(cudaGetLastError());
+
+    ColumnView cv;
+    cv.ld = n; cv.ncols = P; cv.sorted_io = true;
+    int h_active = P;
+    const int poll = 8;
+    for (int itn = 1; itn <= maxiter; ++itn) {
+        // y = K (r2 / beta)
+        cv.in = r2; cv.out = y; cv.in_scale = inv_beta; cv.active = active;
+        LMC_TRY(op_mvm(op, cv, st));
+        minres_k1_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r1, r2, cs, inv_beta, active, n, pa, nblk);
+        minres_k2_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r2, cs, active, n, pa, pb, nblk);
+        { double* t = r1; r1 = r2; r2 = y; y = t; }   // r1 <- r2 <- y ; old r1 buffer is the next y
+        minres_s1_kernel<<<sblocks, sthreads, 0, st>>>(cs, active, pb, nblk, P);
+        // v = r1 / oldb
+        minres_k3_kernel<<<vgrid, kVecThreads, 0, st>>>(wc, wa, wb, r1, x, cs, active, n, pc, nblk);
+        { double* t = wa; wa = wb; wb = wc; wc = t; }
+        minres_s2_kernel<<<1, 256, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
+        count_launch(5);
+        bool polled = false;
+        if (itn % check_every == 0) {
+            // reference callback: true residual of the columns still running
+            cv.in = x; cv.out = y; cv.in_scale = nullptr; cv.active = active;
+            LMC_TRY(op_mvm(op, cv, st));
+            minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, active, n, pa, nblk);
+            minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
+            count_launch(2);
+            polled = true;
+        }
+        if (polled || itn % poll == 0 || itn == maxiter) {
+            LMC_CHECK(cudaMemcpyAsync(&h_active, n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LMC_CHECK(cudaStreamSynchronize(st));
+            if (h_active == 0) break;
+        }
+    }
+    // final residual of every column (iterative.py:53)
+    cv.in = x; cv.out = y; cv.in_scale = nullptr; cv.active = nullptr;
+    LMC_TRY(op_mvm(op, cv, st));
+    minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, nullptr, n, pa, nblk);
+    minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
+    minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(x, perm, n, X, ld);
+    count_launch(3);
+    LMC_CHECK(cudaGetLastError());
+    std::vector<ColState> h((size_t)P);
+    LMC_CHECK(cudaMemcpyAsync(h.data(), cs, sizeof(ColState) * P, cudaMemcpyDeviceToHost, st));
+    LMC_CHECK(cudaStreamSynchronize(st));
+    for (int c = 0; c < P; ++c) {
+        if (iters) iters[c] = h[c].itn;
+        if (resid) resid[c] = h[c].resid;
+        if (istop) istop[c] = h[c].istop;
+    }
+    return 0;
+}
+
+}  // namespace lmc

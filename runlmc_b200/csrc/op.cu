@@ -1,0 +1,80 @@
+// Operator lifetime, parameter upload and the fused MVM pipeline
+//   K~ V = W ( sum_q B_q (x) T_q ) W^T V + diag(noise) V
+// (reference: SumMatrix.matvec over the tree assembled by gen_grid_kernel,
+// runlmc/lmc/grid_kernel.py:49-74 and 126-136, call stack in SURVEY.md 3.2).
+// All three reference representations (sum / bt / slfm) are the same matrix;
+// here the sum over q is applied per frequency bin between ONE forward and ONE
+// inverse transform per output instead of Q*D transform pairs.
+#include "op.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace lmc {
+
+static std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+const char* get_error() { return g_err.c_str(); }
+unsigned long long g_launches = 0;
+
+static const size_t kSpectrumTileBytes = 96ull << 20;  // keep the FFT working set near L2 size
+
+int op_ensure_workspace(lmc_op* op) {
+    if (op->G) return 0;
+    const size_t per_pair = sizeof(cplx) * (size_t)op->D * op->emb.bins;
+    int tile = (int)std::max<size_t>(1, kSpectrumTileBytes / per_pair);
+    tile = std::min(tile, 256);
+    op->tile_pairs = tile;
+    const size_t gbytes = sizeof(cplx) * (size_t)tile * op->D * op->emb.grid_pitch;
+    LMC_CHECK(cudaMalloc(&op->G, gbytes));
+    LMC_CHECK(cudaMemset(op->G, 0, gbytes));
+    LMC_CHECK(cudaMalloc(&op->S, per_pair * tile));
+    LMC_CHECK(cudaMemset(op->S, 0, per_pair * tile));
+    return 0;
+}
+
+int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, const double* B,
+                  cudaStream_t st) {
+    LMC_TRY(op->eng.forward(G, op->S, npairs * op->D, st));
+    LMC_TRY(op->eng.mix(op->S, npairs, op->D, Q, spec, B, st));
+    LMC_TRY(op->eng.inverse(op->S, G, npairs * op->D, st));
+    return 0;
+}
+
+int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
+    LMC_TRY(op_ensure_workspace(op));
+    const int npairs = (cv.ncols + 1) / 2;
+    for (int p0 = 0; p0 < npairs; p0 += op->tile_pairs) {
+        const int cnt = std::min(op->tile_pairs, npairs - p0);
+        ColumnView t = cv;
+        const int c0 = 2 * p0;
+        t.in = cv.in + (long)c0 * cv.ld;
+        t.out = cv.out + (long)c0 * cv.ld;
+        t.ncols = std::min(2 * cnt, cv.ncols - c0);
+        t.in_scale = cv.in_scale ? cv.in_scale + c0 : nullptr;
+        t.active = cv.active ? cv.active + c0 : nullptr;
+        LMC_TRY(to_grid(op->ps, t, op->G, st));
+        LMC_TRY(op_grid_apply(op, op->G, cnt, op->Q, op->spec, op->B, st));
+        LMC_TRY(from_grid(op->ps, t, op->G, op->noise, st));
+    }
+    return 0;
+}
+
+}  // namespace lmc
+
+lmc_op::~lmc_op() {
+    lmc::free_points(&ps);
+    cudaFree(spec);
+    cudaFree(B);
+    cudaFree(noise);
+    cudaFree(G);
+    cudaFree(S);
+}
+
+lmc_bttb::~lmc_bttb() {
+    cudaFree(spec);
+    cudaFree(one);
+    cudaFree(G);
+    cudaFree(S);
+}

@@ -1,0 +1,51 @@
+// The fused SKI-LMC operator handle.
+#pragma once
+#include "common.cuh"
+#include "interp.cuh"
+#include "spectral.cuh"
+
+struct lmc_op {
+    int D = 0, ndim = 0, Q = 0;
+    lmc::Embedding emb;
+    lmc::SpectralEngine eng;
+    lmc::PointSet ps;
+    double* spec = nullptr;   // [Q][bins] real circulant spectra / bins (digit-reversed layout)
+    double* B = nullptr;      // [Q][D][D]
+    double* noise = nullptr;  // [D]
+    int spec_cap = 0;         // allocated Q
+    // grid-stage workspace for `tile_pairs` RHS pairs
+    cplx* G = nullptr;        // [tile_pairs][D][grid_pitch]
+    cplx* S = nullptr;        // [tile_pairs][D][bins]
+    int tile_pairs = 0;
+    ~lmc_op();
+};
+
+struct lmc_bttb {
+    lmc::Embedding emb;
+    lmc::SpectralEngine eng;
+    double* spec = nullptr;  // [bins]
+    double* one = nullptr;   // 1x1 identity "B"
+    cplx* G = nullptr;
+    cplx* S = nullptr;
+    int cap_pairs = 0;
+    ~lmc_bttb();
+};
+
+namespace lmc {
+
+int op_ensure_workspace(lmc_op* op);
+// OUT = K~ V for ncols columns described by cv (cv.in / cv.out), noise included
+int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st);
+// same without the noise term and with explicit spectra / mixing matrices
+// (used by the gradient stage); spec/B device pointers, Q kernels
+int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, const double* B,
+                  cudaStream_t st);
+
+int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st);
+
+int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* RINV, long ld, int N,
+               int ntops_extra, const double* tops_extra_host, double* quad, double* trace,
+               double* nquad, double* ntrace, cudaStream_t st);
+
+}  // namespace lmc

@@ -1,0 +1,58 @@
+// Circulant-embedding spectral engine: batched pruned FFT passes + coregionalisation mix.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include <vector>
+
+namespace lmc {
+
+// Geometry of one symmetric block-Toeplitz (BTTB) embedding, ndim <= 3.
+// sizes m_p, embedding mt_p = 2^ceil(log2(2 m_p)) (reference bttb.py:16-19).
+struct Embedding {
+    int ndim = 0;
+    int m[3] = {1, 1, 1};
+    int mt[3] = {1, 1, 1};
+    long cells = 0;       // prod m
+    long bins = 0;        // prod mt  (full complex spectrum; RHS are processed in complex pairs)
+    // 1-D long lines are split four-step style: mt[0] = L1 * L2
+    int L1 = 0, L2 = 0;
+    long grid_pitch = 0;  // allocated cells per (pair, output) grid slab (>= cells)
+};
+
+int embedding_init(Embedding* e, int ndim, const int* sizes);
+
+class SpectralEngine {
+  public:
+    ~SpectralEngine();
+    int init(const Embedding& emb);
+    const Embedding& emb() const { return emb_; }
+
+    // spec[bins] (device, real, scaled by 1/bins, digit-reversed layout) from a
+    // top row top[cells] (device).  Work buffer: bins cplx.
+    int spectrum(const double* top_dev, double* spec_dev, cplx* work, cudaStream_t st);
+
+    // In place on grid slabs G[nslab][grid_pitch] (complex pairs): forward
+    // pruned transform into S[nslab][bins].
+    int forward(const cplx* G, cplx* S, int nslab, cudaStream_t st);
+    // inverse pruned transform S -> G (cropped)
+    int inverse(cplx* S, cplx* G, int nslab, cudaStream_t st);
+
+    // S[pair][D][bins] <- (sum_q F_q[bin] B_q) S[pair][:][bin]   (in place)
+    int mix(cplx* S, int npairs, int D, int Q, const double* spec /*[Q][bins]*/,
+            const double* B /*[Q][D][D] device*/, cudaStream_t st);
+
+    size_t work_elems(int nslab) const { return (size_t)nslab * emb_.bins; }
+
+  private:
+    Embedding emb_;
+    cplx* tw_[3] = {nullptr, nullptr, nullptr};  // per-axis twiddle tables exp(-2 pi i k / mt_p)
+    int tw_n_[3] = {0, 0, 0};
+    FftPlan plan_[3];
+    FftPlan plan1_, plan2_;                       // four-step sub-plans
+};
+
+// real grid vectors X[k][D*m] <-> complex pair slabs Z[ceil(k/2)][D][gpitch]
+int pack_pairs(const double* X, int k, int D, long m, cplx* Z, long gpitch, cudaStream_t st);
+int unpack_pairs(const cplx* Z, long gpitch, double* Y, int k, int D, long m, cudaStream_t st);
+
+}  // namespace lmc

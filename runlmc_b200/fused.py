@@ -1,0 +1,234 @@
+"""Python handle of the fused device operator  K~ = W (sum_q B_q (x) T_q) W^T + D.
+
+One `FusedLMC` replaces the whole operator tree the reference assembles in
+gen_grid_kernel (runlmc/lmc/grid_kernel.py:49-74).  All arithmetic happens in
+liblmc_b200.so; torch is used for device buffers and streams only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+
+
+def _dev(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class FusedLMC:
+    """:param Xs: list of D arrays of input points, each [n_d] or [n_d, ndim]
+    :param grids: list of ndim equispaced 1-D grids (ndim in {1, 2})
+    """
+
+    def __init__(self, Xs, grids):
+        self._h = ctypes.c_void_p()
+        nat.require_cuda()
+        grids = [np.asarray(g, dtype=np.float64) for g in grids]
+        ndim = len(grids)
+        Xs = [np.asarray(X, dtype=np.float64).reshape(len(X), -1) for X in Xs]
+        if any(X.shape[1] != ndim for X in Xs):
+            raise ValueError('input dimension does not match number of grids')
+        for g in grids:
+            if g.ndim != 1:
+                raise ValueError('grid dim {} should be 1'.format(g.ndim))
+            if g.size < 4:
+                raise ValueError('grid size {} must be >=4'.format(g.size))
+        self.D = len(Xs)
+        self.ndim = ndim
+        self.lens = [len(X) for X in Xs]
+        self.n = int(sum(self.lens))
+        self.grid_sizes = [int(g.size) for g in grids]
+        self.m = int(np.prod(self.grid_sizes))
+        sizes = nat.as_i32(self.grid_sizes)
+        origin = nat.as_f64([g[0] for g in grids])
+        delta = nat.as_f64([g[1] - g[0] for g in grids])   # interpolation.py:98
+        lens = nat.as_i32(self.lens)
+        X = nat.as_f64(np.vstack(Xs)) if self.n else np.zeros((0, ndim))
+        nat.check(nat.lib.lmc_op_create(
+            ctypes.byref(self._h), self.D, ndim, nat.host_ptr(sizes),
+            nat.host_ptr(origin), nat.host_ptr(delta), nat.host_ptr(lens),
+            nat.host_ptr(X)))
+        self.Q = 0
+        self.shape = (self.n, self.n)
+        self.dtype = np.float64
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            try:
+                nat.lib.lmc_op_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+
+    # ---- parameters ------------------------------------------------------
+    def set_params(self, tops, Bs, noise):
+        """tops: Q arrays of kernel values on the grid (any shape with m
+        entries); Bs: Q (D, D) coregionalisation matrices; noise: (D,)."""
+        tops = nat.as_f64(np.array([np.asarray(t, dtype=np.float64).ravel()
+                                    for t in tops]))
+        Bs = nat.as_f64(np.array(Bs))
+        noise = nat.as_f64(noise)
+        Q = tops.shape[0]
+        if tops.shape != (Q, self.m):
+            raise ValueError('tops shape {} != {}'.format(tops.shape, (Q, self.m)))
+        if Bs.shape != (Q, self.D, self.D):
+            raise ValueError('B shape {} != {}'.format(Bs.shape, (Q, self.D, self.D)))
+        if noise.shape != (self.D,):
+            raise ValueError('noise shape {} != {}'.format(noise.shape, (self.D,)))
+        nat.check(nat.lib.lmc_op_set_params(
+            self._h, Q, nat.host_ptr(tops), nat.host_ptr(Bs), nat.host_ptr(noise)))
+        self.Q = Q
+
+    def perm(self):
+        p = np.empty(self.n, dtype=np.int32)
+        nat.check(nat.lib.lmc_op_perm(self._h, nat.host_ptr(p)))
+        return p
+
+    # ---- products --------------------------------------------------------
+    def _block(self, V):
+        V = nat.as_f64(V)
+        if V.ndim == 1:
+            V = V.reshape(1, -1)
+        if V.ndim != 2 or V.shape[1] != self.n:
+            raise ValueError('expected block of shape (P, {}), got {}'.format(self.n, V.shape))
+        return V
+
+    def mvm(self, V):
+        """K~ applied to the rows of V ([P, n] or [n]); host in, host out."""
+        single = np.ndim(V) == 1
+        V = self._block(V)
+        out = np.empty_like(V)
+        nat.check(nat.lib.lmc_mvm_host(self._h, nat.host_ptr(V), self.n,
+                                        V.shape[0], nat.host_ptr(out)))
+        return out[0] if single else out
+
+    def matvec(self, x):
+        return self.mvm(np.asarray(x, dtype=np.float64).reshape(-1))
+
+    def matmat(self, X):
+        return self.mvm(np.asarray(X, dtype=np.float64).T).T
+
+    def mvm_device(self, V, out=None):
+        """V: torch float64 CUDA tensor [P, n] (row stride = n). Stream ordered."""
+        torch = nat.require_cuda()
+        assert V.is_cuda and V.dtype == torch.float64 and V.is_contiguous()
+        if out is None:
+            out = torch.empty_like(V)
+        nat.check(nat.lib.lmc_mvm(self._h, _dev(V), V.shape[1], V.shape[0],
+                                   _dev(out), nat.current_stream_ptr()))
+        return out
+
+    def to_grid_device(self, V):
+        torch = nat.require_cuda()
+        G = torch.empty((V.shape[0], self.D * self.m), dtype=torch.float64, device=V.device)
+        nat.check(nat.lib.lmc_to_grid(self._h, _dev(V), V.shape[1], V.shape[0],
+                                       _dev(G), nat.current_stream_ptr()))
+        return G
+
+    def grid_mvm_device(self, G):
+        torch = nat.require_cuda()
+        out = torch.empty_like(G)
+        nat.check(nat.lib.lmc_grid_mvm(self._h, _dev(G), G.shape[0], _dev(out),
+                                        nat.current_stream_ptr()))
+        return out
+
+    def from_grid_device(self, G):
+        torch = nat.require_cuda()
+        out = torch.empty((G.shape[0], self.n), dtype=torch.float64, device=G.device)
+        nat.check(nat.lib.lmc_from_grid(self._h, _dev(G), G.shape[0], _dev(out),
+                                         self.n, nat.current_stream_ptr()))
+        return out
+
+    # ---- solves ----------------------------------------------------------
+    def minres(self, RHS, tol=1e-4, maxiter=None, check_every=100):
+        """Batched Iterative.solve (approx/iterative.py:24-62) on the rows of
+        RHS.  Returns (X, iters, resid, istop)."""
+        RHS = self._block(RHS)
+        P = RHS.shape[0]
+        X = np.empty_like(RHS)
+        iters = np.zeros(P, dtype=np.int32)
+        resid = np.zeros(P, dtype=np.float64)
+        istop = np.zeros(P, dtype=np.int32)
+        nat.check(nat.lib.lmc_minres_host(
+            self._h, nat.host_ptr(RHS), self.n, P, nat.host_ptr(X), float(tol),
+            int(self.n if maxiter is None else maxiter), int(check_every),
+            nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(istop)))
+        return X, iters, resid, istop
+
+    def minres_device(self, RHS, tol=1e-4, maxiter=None, check_every=100):
+        torch = nat.require_cuda()
+        assert RHS.is_cuda and RHS.dtype == torch.float64 and RHS.is_contiguous()
+        P = RHS.shape[0]
+        X = torch.empty_like(RHS)
+        iters = np.zeros(P, dtype=np.int32)
+        resid = np.zeros(P, dtype=np.float64)
+        istop = np.zeros(P, dtype=np.int32)
+        nat.check(nat.lib.lmc_minres(
+            self._h, _dev(RHS), RHS.shape[1], P, _dev(X), float(tol),
+            int(self.n if maxiter is None else maxiter), int(check_every),
+            nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(istop),
+            nat.current_stream_ptr()))
+        return X, iters, resid, istop
+
+    # ---- gradient contractions --------------------------------------------
+    def grad_grams_device(self, alpha, R, RINV, extra_tops=()):
+        """alpha [n], R/RINV [N, n] CUDA tensors; extra_tops: derivative tops.
+        Returns (quad[T,D,D], trace[T,D,D], nquad[D], ntrace[D]) numpy, T = Q + len(extra_tops)."""
+        torch = nat.require_cuda()
+        N = 0 if R is None else R.shape[0]
+        ext = nat.as_f64(np.array([np.asarray(t, dtype=np.float64).ravel() for t in extra_tops])
+                         if len(extra_tops) else np.zeros((0, self.m)))
+        T = self.Q + ext.shape[0]
+        D = self.D
+        quad = np.zeros((T, D, D))
+        trace = np.zeros((T, D, D))
+        nquad = np.zeros(D)
+        ntrace = np.zeros(D)
+        assert alpha.is_contiguous() and alpha.dtype == torch.float64
+        if N:
+            assert R.is_contiguous() and RINV.is_contiguous() and R.shape == RINV.shape
+        nat.check(nat.lib.lmc_grad_grams(
+            self._h, _dev(alpha), _dev(R) if N else None, _dev(RINV) if N else None,
+            self.n, N, ext.shape[0], nat.host_ptr(ext) if ext.shape[0] else None,
+            nat.host_ptr(quad), nat.host_ptr(trace), nat.host_ptr(nquad), nat.host_ptr(ntrace),
+            nat.current_stream_ptr()))
+        return quad, trace, nquad, ntrace
+
+    def grad_grams(self, alpha, R, RINV, extra_tops=()):
+        torch = nat.require_cuda()
+        dev = torch.device('cuda')
+        a = torch.as_tensor(nat.as_f64(alpha), device=dev)
+        Rt = torch.as_tensor(nat.as_f64(R), device=dev) if len(R) else None
+        Ri = torch.as_tensor(nat.as_f64(RINV), device=dev) if len(R) else None
+        return self.grad_grams_device(a, Rt, Ri, extra_tops)
+
+
+def assemble_gradients(coreg_vecs, coreg_mats, kernel_param_counts, N, quad, trace, nquad, ntrace):
+    """Chain rule of ApproxLMCLikelihood's gradient families
+    (runlmc/lmc/likelihood.py:48-96) from the Gram matrices:
+    dL/dtheta = 0.5 (<C, quad_t> - <C, trace_t> / N)  (derivative.py:5-6,
+    stochastic_deriv.py:69-78).
+
+    Returns (coreg_vec_grads, coreg_diag_grads, kernel_grads, noise_grad)."""
+    Q = len(coreg_vecs)
+    D = len(nquad)
+    Nn = max(N, 1)
+    M = [0.5 * (quad[t] - trace[t] / Nn) for t in range(quad.shape[0])]
+    cv, cd, kg = [], [], []
+    for q, a in enumerate(coreg_vecs):
+        a = np.atleast_2d(a)
+        g = np.zeros(a.shape)
+        for i, ai in enumerate(a):
+            # dA = e_j ai^T + ai e_j^T  ->  <dA, M> = M[j,:].ai + ai.M[:,j]
+            g[i] = M[q].dot(ai) + ai.dot(M[q])
+        cv.append(g)
+        cd.append(np.diag(M[q]).copy())                 # C = E_ii
+    t = Q
+    for q in range(Q):
+        gq = []
+        for _ in range(kernel_param_counts[q]):
+            gq.append(float(np.sum(coreg_mats[q] * M[t])))   # C = B_q, top = dk_q/dtheta
+            t += 1
+        kg.append(gq)
+    noise = 0.5 * (np.asarray(nquad) - np.asarray(ntrace) / Nn)
+    return cv, cd, kg, noise
