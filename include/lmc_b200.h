@@ -37,6 +37,14 @@ const char* lmc_last_error(void);
 /* number of CUDA kernels launched by this library so far in this process */
 unsigned long long lmc_launch_count(void);
 
+/* Optional per-kernel-family device timing (CUDA events on the launching stream).
+ * lmc_profile_begin() starts recording; lmc_profile_end() synchronises and returns,
+ * per family, total milliseconds and launch counts (arrays of lmc_profile_ncat()). */
+int lmc_profile_ncat(void);
+const char* lmc_profile_name(int cat);
+int lmc_profile_begin(void);
+int lmc_profile_end(double* ms, int* counts);
+
 /* ---- fused operator ------------------------------------------------------
  * Replaces the operator tree built by gen_grid_kernel (lmc/grid_kernel.py:49-74):
  * SumMatrix([GridKernel(SKI(sum|bt|slfm grid kernel, W, W^T)), Diag(noise)]).
@@ -84,6 +92,18 @@ int lmc_minres(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev,
 int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host,
                     double tol, int maxiter, int check_every, int* iters_host,
                     double* resid_host, int* istop_host);
+
+/* Same solver for an operator tree composed by the caller (the runlmc.linalg mirror
+ * classes): for every product the solver writes the [P][n] input block to
+ * scratch_in_dev, calls apply_cb(ctx) -- which must leave K * scratch_in in
+ * scratch_out_dev, on the same stream -- and reads scratch_out_dev.            */
+int lmc_minres_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratch_in_dev,
+                       double* scratch_out_dev, const double* RHS_dev, long ld, int P, double* X_dev,
+                       double tol, int maxiter, int check_every, int* iters_host, double* resid_host,
+                       int* istop_host, void* stream);
+/* out = sum_c sum_i A[c][i] * B[c][i]  (the dot products of StochasticDeriv, stochastic_deriv.py:69-78) */
+int lmc_block_dot(const double* A_dev, long lda, const double* B_dev, long ldb, long n, int ncols,
+                  double* out_host, void* stream);
 
 /* ---- gradient contractions -------------------------------------------------
  * Everything StochasticDeriv.derivative (stochastic_deriv.py:69-78) needs for all

@@ -36,6 +36,10 @@ SIGNATURES = {
     'lmc_version': (_i, []),
     'lmc_last_error': (ctypes.c_char_p, []),
     'lmc_launch_count': (ctypes.c_ulonglong, []),
+    'lmc_profile_ncat': (_i, []),
+    'lmc_profile_name': (ctypes.c_char_p, [_i]),
+    'lmc_profile_begin': (_i, []),
+    'lmc_profile_end': (_i, [_p, _p]),
     'lmc_op_create': (_i, [ctypes.POINTER(_p), _i, _i, _p, _p, _p, _p, _p]),
     'lmc_op_destroy': (_i, [_p]),
     'lmc_op_set_params': (_i, [_p, _i, _p, _p, _p]),
@@ -50,6 +54,8 @@ SIGNATURES = {
     'lmc_from_grid': (_i, [_p, _p, _i, _p, _l, _p]),
     'lmc_minres': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
     'lmc_minres_host': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p]),
+    'lmc_minres_generic': (_i, [_p, _p, _l, _p, _p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
+    'lmc_block_dot': (_i, [_p, _l, _p, _l, _l, _i, _p, _p]),
     'lmc_grad_grams': (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p]),
     'lmc_bttb_create': (_i, [ctypes.POINTER(_p), _i, _p, _p]),
     'lmc_bttb_destroy': (_i, [_p]),
@@ -100,3 +106,17 @@ def require_cuda():
 def current_stream_ptr():
     torch = require_cuda()
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def profile_begin():
+    check(lib.lmc_profile_begin())
+
+
+def profile_end():
+    """-> {family: (total_ms, launches)} since profile_begin()."""
+    ncat = lib.lmc_profile_ncat()
+    ms = np.zeros(ncat)
+    cnt = np.zeros(ncat, dtype=np.int32)
+    check(lib.lmc_profile_end(host_ptr(ms), host_ptr(cnt)))
+    return {lib.lmc_profile_name(c).decode(): (float(ms[c]), int(cnt[c]))
+            for c in range(ncat) if cnt[c]}

@@ -41,6 +41,22 @@ const char* get_error();
 extern unsigned long long g_launches;
 inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
 
+// Optional per-kernel-family timing with CUDA events on the launching stream
+// (bench.py's roofline figures come from here).  Disabled => zero overhead.
+enum ProfCat {
+    PROF_TO_GRID = 0, PROF_FFT_FWD_CONTIG, PROF_FFT_FWD_STRIDED, PROF_MIX, PROF_FFT_INV_STRIDED,
+    PROF_FFT_INV_CONTIG, PROF_FROM_GRID, PROF_MINRES_VEC, PROF_MINRES_SCALAR, PROF_GRAD, PROF_OTHER,
+    PROF_NCAT
+};
+extern bool g_prof_on;
+void prof_begin(int cat, cudaStream_t st);
+void prof_end(int cat, cudaStream_t st);
+struct ProfScope {
+    int cat; cudaStream_t st;
+    ProfScope(int c, cudaStream_t s) : cat(c), st(s) { if (g_prof_on) prof_begin(cat, st); }
+    ~ProfScope() { if (g_prof_on) prof_end(cat, st); }
+};
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int ilog2(unsigned v) { int k = 0; while ((1u << k) < v) ++k; return k; }
 

@@ -132,6 +132,7 @@ struct GradBuf {
 static int cross_spectrum(int D, const cplx* U, const cplx* Z, long bins, int npairs, double* C,
                           int accumulate, cudaStream_t st) {
     const unsigned grid = (unsigned)ceil_div(bins, 128);
+    ProfScope prof(PROF_GRAD, st);
     switch (D) {
 #define LMC_CS_CASE(DD)                                                                        \
     case DD:                                                                                   \

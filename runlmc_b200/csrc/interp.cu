@@ -491,6 +491,7 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     if (cv.ncols == 0) return 0;
     InterpArgs a = make_args(ps, cv);
     a.G = G;
+    ProfScope prof(PROF_TO_GRID, st);
     const bool perm = !(cv.sorted_io || ps.identity);
     if (ps.ndim == 1) {
         const int threads = 256, TC = threads - 3, PT = 4;
@@ -524,6 +525,7 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
     if (cv.ncols == 0) return 0;
     InterpArgs a = make_args(ps, cv);
     a.Gc = G;
+    ProfScope prof(PROF_FROM_GRID, st);
     a.noise = noise;
     const bool perm = !(cv.sorted_io || ps.identity);
     if (ps.ndim == 1) {

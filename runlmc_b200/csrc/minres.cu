@@ -300,6 +300,65 @@ __global__ void __launch_bounds__(kVecThreads) minres_finish_kernel(
     }
 }
 
+// Y = s * X per column (materialises v = r2 / beta for callback operators)
+__global__ void __launch_bounds__(kVecThreads) scale_cols_kernel(const double* __restrict__ X,
+                                                                const double* __restrict__ scale, long n,
+                                                                double* Y) {
+    const int col = blockIdx.y;
+    const double s = scale ? scale[col] : 1.0;
+    const long base = (long)blockIdx.x * kVecChunk;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) Y[(long)col * n + i] = __dmul_rn(s, X[(long)col * n + i]);
+    }
+}
+
+// The product the solver iterates with: out = A (in * in_scale) on [P][n] blocks
+struct MinresOperator {
+    long n = 0;
+    const int* perm = nullptr;  // solver order -> caller order (nullptr = identity)
+    virtual int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
+                      cudaStream_t st) = 0;
+    virtual ~MinresOperator() {}
+};
+
+struct FusedOperator : MinresOperator {
+    lmc_op* op;
+    explicit FusedOperator(lmc_op* o) : op(o) {
+        n = o->ps.n;
+        perm = o->ps.identity ? nullptr : o->ps.perm;
+    }
+    int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
+              cudaStream_t st) override {
+        ColumnView cv;
+        cv.in = in; cv.out = out; cv.ld = n; cv.ncols = P; cv.sorted_io = true;
+        cv.in_scale = in_scale; cv.active = active;
+        return op_mvm(op, cv, st);
+    }
+};
+
+// Operator trees composed on the Python side: the solver fills `scratch_in`,
+// calls back, and reads `scratch_out` (both [P][n] device blocks).
+struct CallbackOperator : MinresOperator {
+    int (*cb)(void*);
+    void* ctx;
+    double* scratch_in;
+    double* scratch_out;
+    int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
+              cudaStream_t st) override {
+        (void)active;
+        const dim3 grid((unsigned)ceil_div(n, kVecChunk), (unsigned)P);
+        scale_cols_kernel<<<grid, kVecThreads, 0, st>>>(in, in_scale, n, scratch_in);
+        count_launch();
+        LMC_CHECK(cudaGetLastError());
+        const int rc = cb(ctx);
+        if (rc != 0) { set_error("operator callback failed"); return 3; }
+        LMC_CHECK(cudaMemcpyAsync(out, scratch_out, sizeof(double) * (size_t)P * n,
+                                  cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+};
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -307,12 +366,12 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
-int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
-                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st) {
+static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, double* X, double tol,
+                       int maxiter, int check_every, int* iters, double* resid, int* istop,
+                       cudaStream_t st) {
     LMC_REQUIRE(P >= 1, "need at least one right-hand side");
-    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
     LMC_REQUIRE(maxiter >= 1 && check_every >= 1, "maxiter/check_every must be positive");
-    const long n = op->ps.n;
+    const long n = A.n;
     LMC_REQUIRE(ld >= n, "leading dimension < n");
     const int nblk = ceil_div(n, kVecChunk);
     const double rtol = std::fmin(1e-10, tol);
@@ -333,7 +392,7 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
     double* inv_beta = invb.as<double>();
     int* active = act.as<int>();
     int* n_active = nact.as<int>();
-    const int* perm = op->ps.identity ? nullptr : op->ps.perm;
+    const int* perm = A.perm;
     const dim3 vgrid((unsigned)nblk, (unsigned)P);
     const int sthreads = 128, sblocks = ceil_div(P, sthreads);
 
@@ -342,28 +401,36 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
     count_launch(2);
     LMC_CHECK(cudaGetLastError());
 
-    ColumnView cv;
-    cv.ld = n; cv.ncols = P; cv.sorted_io = true;
     int h_active = P;
     const int poll = 8;
     for (int itn = 1; itn <= maxiter; ++itn) {
         // y = K (r2 / beta)
-        cv.in = r2; cv.out = y; cv.in_scale = inv_beta; cv.active = active;
-        LMC_TRY(op_mvm(op, cv, st));
-        minres_k1_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r1, r2, cs, inv_beta, active, n, pa, nblk);
-        minres_k2_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r2, cs, active, n, pa, pb, nblk);
+        LMC_TRY(A.apply(r2, inv_beta, active, y, P, st));
+        {
+            ProfScope prof(PROF_MINRES_VEC, st);
+            minres_k1_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r1, r2, cs, inv_beta, active, n, pa, nblk);
+            minres_k2_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r2, cs, active, n, pa, pb, nblk);
+        }
         { double* t = r1; r1 = r2; r2 = y; y = t; }   // r1 <- r2 <- y ; old r1 buffer is the next y
-        minres_s1_kernel<<<sblocks, sthreads, 0, st>>>(cs, active, pb, nblk, P);
-        // v = r1 / oldb
-        minres_k3_kernel<<<vgrid, kVecThreads, 0, st>>>(wc, wa, wb, r1, x, cs, active, n, pc, nblk);
+        {
+            ProfScope prof(PROF_MINRES_SCALAR, st);
+            minres_s1_kernel<<<sblocks, sthreads, 0, st>>>(cs, active, pb, nblk, P);
+        }
+        {
+            // v = r1 / oldb
+            ProfScope prof(PROF_MINRES_VEC, st);
+            minres_k3_kernel<<<vgrid, kVecThreads, 0, st>>>(wc, wa, wb, r1, x, cs, active, n, pc, nblk);
+        }
         { double* t = wa; wa = wb; wb = wc; wc = t; }
-        minres_s2_kernel<<<1, 256, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
+        {
+            ProfScope prof(PROF_MINRES_SCALAR, st);
+            minres_s2_kernel<<<1, 256, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
+        }
         count_launch(5);
         bool polled = false;
         if (itn % check_every == 0) {
             // reference callback: true residual of the columns still running
-            cv.in = x; cv.out = y; cv.in_scale = nullptr; cv.active = active;
-            LMC_TRY(op_mvm(op, cv, st));
+            LMC_TRY(A.apply(x, nullptr, active, y, P, st));
             minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, active, n, pa, nblk);
             minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
             count_launch(2);
@@ -376,8 +443,7 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
         }
     }
     // final residual of every column (iterative.py:53)
-    cv.in = x; cv.out = y; cv.in_scale = nullptr; cv.active = nullptr;
-    LMC_TRY(op_mvm(op, cv, st));
+    LMC_TRY(A.apply(x, nullptr, nullptr, y, P, st));
     minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, nullptr, n, pa, nblk);
     minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
     minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(x, perm, n, X, ld);
@@ -394,4 +460,67 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
     return 0;
 }
 
+int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st) {
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+    FusedOperator A(op);
+    return minres_core(A, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st);
+}
+
+// sum over a [ncols][n] block of A .* B, two-stage deterministic
+__global__ void __launch_bounds__(kVecThreads) block_dot_kernel(const double* __restrict__ A,
+                                                               const double* __restrict__ B, long lda,
+                                                               long ldb, long n, double* part, int nblk) {
+    const int col = blockIdx.y;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) acc = fma(A[(long)col * lda + i], B[(long)col * ldb + i], acc);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
 }  // namespace lmc
+
+using namespace lmc;
+
+extern "C" {
+
+int lmc_minres_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratch_in_dev,
+                       double* scratch_out_dev, const double* RHS_dev, long ld, int P, double* X_dev,
+                       double tol, int maxiter, int check_every, int* iters_host, double* resid_host,
+                       int* istop_host, void* stream) {
+    LMC_REQUIRE(apply_cb && scratch_in_dev && scratch_out_dev && RHS_dev && X_dev, "null argument");
+    LMC_REQUIRE(n >= 1 && ld >= n, "bad block shape");
+    CallbackOperator A;
+    A.n = n; A.perm = nullptr; A.cb = apply_cb; A.ctx = ctx;
+    A.scratch_in = scratch_in_dev; A.scratch_out = scratch_out_dev;
+    return minres_core(A, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+                       istop_host, (cudaStream_t)stream);
+}
+
+int lmc_block_dot(const double* A_dev, long lda, const double* B_dev, long ldb, long n, int ncols,
+                  double* out_host, void* stream) {
+    LMC_REQUIRE(A_dev && B_dev && out_host && n >= 1 && ncols >= 0, "bad argument");
+    *out_host = 0.0;
+    if (ncols == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = ceil_div(n, kVecChunk);
+    DevBuf part;
+    LMC_TRY(part.alloc(sizeof(double) * (size_t)ncols * nblk));
+    block_dot_kernel<<<dim3((unsigned)nblk, (unsigned)ncols), kVecThreads, 0, st>>>(
+        A_dev, B_dev, lda, ldb, n, part.as<double>(), nblk);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    std::vector<double> h((size_t)ncols * nblk);
+    LMC_CHECK(cudaMemcpyAsync(h.data(), part.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+    LMC_CHECK(cudaStreamSynchronize(st));
+    double s = 0.0;
+    for (double v : h) s += v;
+    *out_host = s;
+    return 0;
+}
+
+}  // extern "C"

@@ -17,6 +17,25 @@ void set_error(const std::string& s) { g_err = s; }
 const char* get_error() { return g_err.c_str(); }
 unsigned long long g_launches = 0;
 
+bool g_prof_on = false;
+namespace {
+struct ProfRec { int cat; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof_recs;
+cudaEvent_t g_prof_open[PROF_NCAT];
+}  // namespace
+void prof_begin(int cat, cudaStream_t st) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_prof_open[cat] = e;
+}
+void prof_end(int cat, cudaStream_t st) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    g_prof_recs.push_back({cat, g_prof_open[cat], e});
+}
+
 static const size_t kSpectrumTileBytes = 96ull << 20;  // keep the FFT working set near L2 size
 
 int op_ensure_workspace(lmc_op* op) {
@@ -77,4 +96,34 @@ lmc_bttb::~lmc_bttb() {
     cudaFree(one);
     cudaFree(G);
     cudaFree(S);
+}
+
+extern "C" {
+static const char* kProfNames[lmc::PROF_NCAT] = {
+    "to_grid", "fft_fwd_contig", "fft_fwd_strided", "mix", "fft_inv_strided", "fft_inv_contig",
+    "from_grid", "minres_vec", "minres_scalar", "grad", "other"};
+int lmc_profile_ncat(void) { return lmc::PROF_NCAT; }
+const char* lmc_profile_name(int cat) { return (cat >= 0 && cat < lmc::PROF_NCAT) ? kProfNames[cat] : ""; }
+int lmc_profile_begin(void) {
+    for (auto& r : lmc::g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    lmc::g_prof_recs.clear();
+    lmc::g_prof_on = true;
+    return 0;
+}
+// ms[cat] = total device time, counts[cat] = launches, since lmc_profile_begin()
+int lmc_profile_end(double* ms, int* counts) {
+    lmc::g_prof_on = false;
+    LMC_CHECK(cudaDeviceSynchronize());
+    for (int c = 0; c < lmc::PROF_NCAT; ++c) { ms[c] = 0.0; counts[c] = 0; }
+    for (auto& r : lmc::g_prof_recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[r.cat] += t;
+        counts[r.cat] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    lmc::g_prof_recs.clear();
+    return 0;
+}
 }

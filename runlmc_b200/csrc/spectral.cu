@@ -186,6 +186,8 @@ static int launch_pass(PassArgs a, bool strided, bool inv, cudaStream_t st) {
     const size_t smem = (size_t)nl * a.pitch * sizeof(cplx);
     const int work = nl * a.L / 8;
     const int threads = work >= 512 ? 512 : (work >= 256 ? 256 : (work >= 128 ? 128 : 64));
+    ProfScope prof(inv ? (strided ? PROF_FFT_INV_STRIDED : PROF_FFT_INV_CONTIG)
+                       : (strided ? PROF_FFT_FWD_STRIDED : PROF_FFT_FWD_CONTIG), st);
 #define LMC_LAUNCH_PASS(S, I)                                                               \
     do {                                                                                    \
         static bool attr_set = false;                                                       \
@@ -612,6 +614,7 @@ int SpectralEngine::mix(cplx* S, int npairs, int D, int Q, const double* spec, c
     const long bins = emb_.bins;
     dim3 grid((unsigned)ceil_div(bins, 128), (unsigned)npairs);
     const size_t smem = sizeof(double) * (size_t)Q * D * D;
+    ProfScope prof(PROF_MIX, st);
     switch (D) {
 #define LMC_MIX_CASE(DD)                                                              \
     case DD:                                                                          \

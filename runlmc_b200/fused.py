@@ -25,9 +25,10 @@ class FusedLMC:
         nat.require_cuda()
         grids = [np.asarray(g, dtype=np.float64) for g in grids]
         ndim = len(grids)
-        Xs = [np.asarray(X, dtype=np.float64).reshape(len(X), -1) for X in Xs]
-        if any(X.shape[1] != ndim for X in Xs):
+        Xs = [np.asarray(X, dtype=np.float64) for X in Xs]
+        if any(X.size != len(X) * ndim for X in Xs):
             raise ValueError('input dimension does not match number of grids')
+        Xs = [X.reshape(len(X), ndim) for X in Xs]
         for g in grids:
             if g.ndim != 1:
                 raise ValueError('grid dim {} should be 1'.format(g.ndim))

@@ -1,0 +1,71 @@
+"""Mirror of runlmc/lmc/stochastic_deriv.py: Hutchinson-probe derivative service."""
+import numpy as np
+
+from .derivative import Derivative
+from ..approx.iterative import Iterative, fused_of, solve_block
+from .. import _native as nat
+from .. import device as dev
+
+
+class StochasticDerivService:
+    """:param metrics: a Metrics instance or None, :param pool: pool for operator
+    trees the fused path does not cover, :param n_it: number of probes,
+    :param tol: solver tolerance (stochastic_deriv.py:27-31)."""
+
+    def __init__(self, metrics, pool, n_it, tol):
+        self.metrics = metrics
+        self._pool = pool
+        self._n_it = n_it
+        self._tol = tol
+
+    def generate(self, K, y, rs=None):
+        """Draw n_it Rademacher probes from the GLOBAL numpy RNG exactly like the
+        reference (stochastic_deriv.py:35) -- or take host-supplied `rs` -- and
+        solve the n_it + 1 systems as one multi-RHS MINRES on the device."""
+        n = K.shape[0]
+        if rs is None:
+            rs = np.random.randint(0, 2, (self._n_it, n)) * 2 - 1
+        rs = np.asarray(rs)
+        RHS = np.vstack([np.asarray(y, dtype=np.float64).reshape(1, -1), rs.astype(np.float64)])
+        X, iters, resid, _ = solve_block(K, RHS, tol=self._tol)
+        if self.metrics is not None:
+            self.metrics.iterations.append(np.mean(iters))
+            self.metrics.solv_error.append(np.mean(resid))
+        return StochasticDeriv(X[0], rs, list(X[1:]), self._n_it)
+
+    def _concurrent_solve(self, ls):
+        return self._pool.starmap(Iterative.solve, ls)
+
+
+class StochasticDeriv(Derivative):
+    """Derivatives from alpha = K^-1 y and the probe solves K^-1 r_i
+    (stochastic_deriv.py:55-78)."""
+
+    def __init__(self, alpha, rs, inv_rs, n_it):
+        self.alpha = alpha
+        self._rs = rs
+        self._inv_rs = inv_rs
+        self._n_it = n_it
+        self._dev_cache = None
+
+    def _dev(self):
+        if self._dev_cache is None:
+            self._dev_cache = (dev.to_device(np.asarray(self.alpha).reshape(1, -1)),
+                               dev.to_device(np.asarray(self._rs, dtype=np.float64)),
+                               dev.to_device(np.asarray(self._inv_rs, dtype=np.float64)))
+        return self._dev_cache
+
+    @staticmethod
+    def _dot(A, B):
+        out = np.zeros(1)
+        nat.check(nat.lib.lmc_block_dot(dev.ptr(A), A.shape[1], dev.ptr(B), B.shape[1], A.shape[1],
+                                        A.shape[0], nat.host_ptr(out), dev.stream()))
+        return float(out[0])
+
+    def d_normal_quadratic(self, dKdt):
+        a, _, _ = self._dev()
+        return self._dot(a, dKdt._apply_dev(a))
+
+    def d_logdet_K(self, dKdt):
+        _, R, Rinv = self._dev()
+        return self._dot(Rinv, dKdt._apply_dev(R)) / self._n_it

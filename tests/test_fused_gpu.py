@@ -107,21 +107,33 @@ def test_linearity_and_symmetry_large():
     assert float(torch.dot(V[0], KV[0])) > 0
 
 
+# MINRES parity.  Lanczos amplifies ulp-level differences in the operator: the
+# reference run with two of its own equivalent representations ('sum' vs 'bt')
+# already differs by 1e-3..1e-1 in mid-convergence iterates (k ~ 25) on these
+# problems, so iterates are compared (a) tightly at small fixed iteration
+# counts, (b) tightly at larger counts on a well-conditioned problem, and (c)
+# at convergence within the solver tolerance.
+SOLVE_TOL = 1e-5     # relative agreement of converged solutions (solver tol = 1e-4 absolute residual)
+
+
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
 def test_minres_against_reference_golden(name):
     from test_oracle_golden import GOLDEN_PROBLEMS
     g = load_golden(name)
     prob = GOLDEN_PROBLEMS[name]()
     op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
     RHS = np.vstack([prob.y[None, :], g['probes']])
     X, iters, resid, istop = op.minres(RHS, tol=1e-4)
     want = np.vstack([g['alpha'][None, :], g['inv_probes']])
-    # same stopping behaviour as scipy + reference wrapper: the reference's
-    # iteration count for y is recorded; allow +-1 for borderline stop tests
-    assert abs(int(iters[0]) - int(g['solve_y_ctr'])) <= 1
-    for x, w in zip(X, want):
-        assert rel_err(x, w) < 1e-6
-    assert abs(resid[0] - float(g['solve_y_err'])) <= 0.05 * float(g['solve_y_err']) + 1e-9
+    ref_it = int(g['solve_y_ctr'])
+    assert abs(int(iters[0]) - ref_it) <= max(3, 0.03 * ref_it)
+    for b, x, w, r in zip(RHS, X, want, resid):
+        assert rel_err(x, w) < SOLVE_TOL
+        ref_res = np.linalg.norm(b - ref.matvec(w))
+        # reported residual is the true residual, and as good as the reference's
+        assert abs(r - np.linalg.norm(b - ref.matvec(x))) <= 1e-9 + 1e-6 * r
+        assert r <= max(1e-4, 3 * ref_res)
 
 
 @pytest.mark.parametrize('name', ['A', '2d_small', 'd_small'])
@@ -131,12 +143,35 @@ def test_minres_fixed_iterations(name):
     op = fused_from_problem(prob)
     _, ref = oracle_from_problem(prob)
     RHS = np.vstack([prob.y[None, :], prob.probes[:3]])
-    for k in (1, 2, 7, 25):
+    for k in (1, 2, 3, 7):
         X, iters, _, istop = op.minres(RHS, tol=1e-4, maxiter=k, check_every=10 ** 6)
         for b, x, it in zip(RHS, X, iters):
             xr, istop_r, itn_r, _ = orc.minres(ref.matvec, b, 1e-10, k)
             assert it == itn_r
-            assert rel_err(x, xr) < 1e-8
+            assert rel_err(x, xr) < 1e-10
+
+
+def well_conditioned_problem():
+    prob = synthetic.make_problem('d_small', seed=21, cells_per_lengthscale=6)
+    prob.noise = np.full(prob.D, 40.0)      # cond(K~) of a few tens
+    return prob
+
+
+def test_minres_fixed_iterations_well_conditioned():
+    """Later iterates: the yardstick is the reference's own spread between two
+    of its equivalent operator representations ('sum' vs 'bt') at the same k."""
+    prob = well_conditioned_problem()
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    _, ref_bt = oracle_from_problem(prob, rep='bt')
+    RHS = np.vstack([prob.y[None, :], prob.probes[:2]])
+    for k in (10, 25):
+        X, iters, _, istop = op.minres(RHS, tol=1e-4, maxiter=k, check_every=10 ** 6)
+        for b, x, it, st in zip(RHS, X, iters, istop):
+            xr, istop_r, itn_r, _ = orc.minres(ref.matvec, b, 1e-10, k)
+            xb, _, _, _ = orc.minres(ref_bt.matvec, b, 1e-10, k)
+            assert it == itn_r and st == istop_r
+            assert rel_err(x, xr) < 1e-10 + 10 * rel_err(xb, xr)
 
 
 def test_minres_zero_rhs_and_mixed():
@@ -144,12 +179,28 @@ def test_minres_zero_rhs_and_mixed():
     op = fused_from_problem(prob)
     RHS = np.vstack([np.zeros(prob.n), prob.y, 1e-3 * prob.probes[0]])
     X, iters, resid, istop = op.minres(RHS, tol=1e-4)
-    assert iters[0] == 0 and np.all(X[0] == 0) and resid[0] == 0
+    # scipy returns x = 0 immediately for a zero right-hand side
+    assert iters[0] == 0 and np.all(X[0] == 0) and resid[0] < 1e-10
     _, ref = oracle_from_problem(prob)
     for b, x, it in zip(RHS[1:], X[1:], iters[1:]):
         xr, ctr, err = orc.iterative_solve(ref.matvec, b, 1e-4)
-        assert abs(int(it) - ctr) <= 1
-        assert rel_err(x, xr) < 1e-6
+        assert abs(int(it) - ctr) <= max(3, 0.03 * ctr)
+        # tol is an absolute residual: loose relative to the 1e-3-scaled rhs
+        assert rel_err(x, xr) < 10 * SOLVE_TOL
+
+
+def test_minres_residual_check_terminates():
+    """The reference's every-100-iterations true-residual test (iterative.py:36-42),
+    exercised with a short period."""
+    prob = well_conditioned_problem()
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    RHS = np.vstack([prob.y[None, :], prob.probes[:3]])
+    X, iters, resid, istop = op.minres(RHS, tol=1e-4, check_every=5)
+    for b, x, it, r, st in zip(RHS, X, iters, resid, istop):
+        xr, ctr, err = orc.iterative_solve(ref.matvec, b, 1e-4, check_every=5)
+        assert abs(int(it) - ctr) <= 5 and it % 5 == 0 and st == 10
+        assert r < 1e-4 and rel_err(x, xr) < SOLVE_TOL
 
 
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
