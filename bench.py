@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the SKI-LMC hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload E] [--impl reference]
+
+One step = one block product K~ V over the workload's right-hand sides
+(y + the Hutchinson probes).  `value` is MVM*RHS per second with V resident in
+HBM; `e2e` is the same metric through the host-buffer C-ABI path (pinned host
+-> device copy of V and device -> host copy of K~V inside the timed region).
+The probes are sharded over the ranks (strong scaling: total work fixed); no
+collective is on the MVM path.  Also reported: per-kernel-family device time
+with the roofline of the dominant family and of the whole product, one full
+stochastic gradient evaluation (solves + all partials), and the CPU oracle
+timed on the host cores.
+
+--impl reference times the reference's own CPU algorithm (the numpy/scipy
+oracle port, one process per core like the reference's Pool.starmap) on a
+bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+os.environ.setdefault('OMP_NUM_THREADS', '1')   # the reference's own setting (benchlib/bench.py:7)
+
+import numpy as np  # noqa: E402
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from runlmc_b200 import synthetic  # noqa: E402
+
+METRIC = 'ski_lmc_mvm_rhs_per_s'
+UNIT = 'MVM*RHS/s'
+CPL = {'A': 4, 'B': 8, 'C': 5, 'D': 8, 'E': 6}     # grid cells per (shortest) lengthscale
+
+
+def workload_desc(name, prob):
+    return {'workload': '%s: D=%d n=%d grid=%s Q=%d probes=%d (SURVEY.md sec.8 config %s)' % (
+        name, prob.D, prob.n, 'x'.join(map(str, prob.grid_sizes)), prob.Q, prob.N, name),
+        'rhs_per_step': prob.N + 1, 'timing': 'CUDA events; inputs (%.2f GB) larger than L2' % (
+            (prob.N + 1) * prob.n * 8 / 1e9)}
+
+
+# --------------------------------------------------------------------------
+# CPU side (oracle port of the reference path)
+# --------------------------------------------------------------------------
+_CPU_OP = None
+
+
+def _cpu_mvm(v):
+    return _CPU_OP.matvec(v)
+
+
+def cpu_reference_rate(prob, steps, warmup, cores=None, budget_s=25.0):
+    """MVM/s of the oracle (= the reference's numpy/scipy arithmetic) with one
+    worker process per core, each step a block of `cores` columns."""
+    global _CPU_OP
+    import multiprocessing as mp
+    from oracle import lmc_oracle as orc
+    cores = cores or len(os.sched_getaffinity(0))
+    spec = orc.KernelSpec(['rbf'] * prob.Q, [[g] for g in prob.gammas], prob.coreg_vecs,
+                          prob.coreg_diags, prob.noise)
+    t0 = time.perf_counter()
+    _CPU_OP = orc.build_operator(spec, prob.Xs, prob.grids, rep='sum')
+    t_build = time.perf_counter() - t0
+    cols = [prob.probes[i % prob.N] for i in range(cores)]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_mvm, cols)
+        done = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_mvm, cols)
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    _CPU_OP = None
+    return {'value': cores * done / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d steps x %d columns (one per core) of the %d-column block; operator build %.1f s not timed'
+                      % (done, cores, prob.N + 1, t_build), 'ms_per_step': 1e3 * dt / done, 'steps': done}
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------
+# roofline bookkeeping (DESIGN.md "Algorithmic bytes")
+# --------------------------------------------------------------------------
+def family_bytes(family, prob, P, bins, gpitch):
+    """Algorithmic HBM bytes of one step for a kernel family."""
+    n, d, D = prob.n, prob.ndim, prob.D
+    pairs = (P + 1) // 2
+    slab = 16.0 * D * pairs
+    if family == 'to_grid':
+        return 8.0 * n * P + 8.0 * d * n + slab * gpitch
+    if family == 'from_grid':
+        return 16.0 * n * P + 8.0 * d * n + slab * gpitch
+    if family in ('fft_fwd_contig', 'fft_inv_contig'):
+        rows = prob.grid_sizes[0] if d == 2 else 1
+        emb_row = bins / (2 * prob.grid_sizes[0]) if d == 2 else bins
+        return slab * (gpitch + rows * emb_row) if d == 2 else slab * (gpitch + bins)
+    if family in ('fft_fwd_strided', 'fft_inv_strided'):
+        return slab * 1.5 * bins
+    if family == 'mix':
+        return slab * 2 * bins
+    return 0.0
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(family):
+    """Per-launch DRAM bytes of the family's kernel from the committed ncu summary, if any."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p)).get(family)
+    return None
+
+
+# --------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    prob = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=CPL[args.workload])
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_rate(prob, steps=3, warmup=1)       # before CUDA is initialised (fork)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from runlmc_b200 import _native as nat
+    from runlmc_b200.fused import FusedLMC
+    from runlmc_b200.distributed import shard_bounds, sharded_gradient
+    dev = torch.device('cuda', local)
+    op = FusedLMC(prob.Xs, prob.grids)
+    op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+    lo, hi = shard_bounds(prob.N, rank, world)
+    rows = [prob.y[None, :]] if rank == 0 else []
+    rows.append(prob.probes[lo:hi])
+    Vh = np.ascontiguousarray(np.vstack(rows))
+    P = Vh.shape[0]
+    V = torch.as_tensor(Vh, device=dev)
+    OUT = torch.empty_like(V)
+    total_units = prob.N + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        op.mvm_device(V, OUT)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = nat.lib.lmc_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        op.mvm_device(V, OUT)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(nat.lib.lmc_launch_count() - l0)
+    clocks = sampler.summary()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_step = ms / args.steps
+    value = total_units * args.steps / (ms / 1e3)
+
+    # ---- end to end through host buffers ----
+    e2e_steps = max(1, min(args.steps, 3))
+    Vp = torch.as_tensor(Vh).pin_memory()
+    Op = torch.empty_like(Vp).pin_memory()
+    Vd = torch.empty_like(V)
+    for _ in range(1):
+        Vd.copy_(Vp, non_blocking=True); op.mvm_device(Vd, OUT); Op.copy_(OUT, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        Vd.copy_(Vp, non_blocking=True)
+        op.mvm_device(Vd, OUT)
+        Op.copy_(OUT, non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = total_units * e2e_steps / (float(t.item()) / 1e3)
+    cnt = torch.tensor([float(P)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+    io_bytes = int(cnt.item()) * prob.n * 8
+
+    # ---- per-family device time (separate pass so events do not perturb `value`) ----
+    nat.profile_begin()
+    for _ in range(args.steps):
+        op.mvm_device(V, OUT)
+    prof = nat.profile_end()
+    bins, gpitch = nat.lib.lmc_op_embed_bins(op._h), nat.lib.lmc_op_grid_cells(op._h)
+    peak, peak_src = peaks()
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    fams = []
+    for k, (m_, c_) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        b = family_bytes(k, prob, P, bins, gpitch)
+        fams.append({'family': k, 'ms_per_step': m_ / args.steps, 'launches_per_step': c_ // args.steps,
+                     'share': m_ / tot, 'alg_gb_per_step': b / 1e9,
+                     'alg_gbs': b / (m_ / args.steps) / 1e6 if m_ else None})
+    top = fams[0]
+    lpl = max(top['launches_per_step'], 1)
+    roofline = {'kernel': top['family'], 'bound': 'hbm', 'achieved': top['alg_gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': (top['alg_gbs'] or 0.0) / peak, 'traffic': ncu_traffic(top['family']),
+                'share_of_step': top['share'], 'alg_bytes_per_launch': top['alg_gb_per_step'] * 1e9 / lpl,
+                'launch_ms': top['ms_per_step'] / lpl, 'peak_source': peak_src}
+    b_mvm = 16.0 * prob.n * P + 8.0 * prob.ndim * prob.n + 8.0 * prob.Q * bins + 8.0 * prob.D
+    roofline_mvm = {'bound': 'hbm', 'alg_bytes_per_step': b_mvm, 'achieved': b_mvm / ms_step / 1e6, 'peak': peak,
+                    'unit': 'GB/s', 'frac': b_mvm / ms_step / 1e6 / peak,
+                    'note': 'whole product vs B_mvm = 16nP + 8dn + 8Q*bins + 8D (SURVEY.md sec.8d), this rank'}
+
+    # ---- one full stochastic gradient evaluation (solves + all partials) ----
+    grad = None
+    if not args.no_grad:
+        barrier()
+        t0 = time.perf_counter()
+        grads, stats = sharded_gradient(op, prob.y, prob.probes, prob.top_grads, prob.coreg_vecs,
+                                        prob.coreg_mats(), tol=1e-4, rank=rank, world=world)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        nparams = sum(np.size(g) for g in grads[0]) + sum(np.size(g) for g in grads[1]) + \
+            sum(len(g) for g in grads[2]) + np.size(grads[3])
+        grad = {'grad_evals_per_s': 1.0 / dt, 'seconds': dt, 'mean_minres_iterations': stats['iterations'],
+                'mean_final_residual': stats['solv_error'], 'hyperparameters': int(nparams),
+                'minres_iter_rhs_per_s': stats['iterations'] * (prob.N + 1) / dt,
+                'includes': 'host->device copies of y/probes, N+1 MINRES solves (tol 1e-4, reference stopping rules), '
+                            'all partial derivatives, allreduce'}
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_desc(args.workload, prob),
+                'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': io_bytes, 'd2h_bytes_per_step': io_bytes,
+                        'steps': e2e_steps}, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+                'roofline_mvm': roofline_mvm, 'kernel_families': fams, 'gradient': grad}
+        if cpu is not None:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    prob = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=CPL[args.workload])
+    r = cpu_reference_rate(prob, steps=args.steps, warmup=args.warmup, budget_s=120.0)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
+            'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': r['steps'], 'warmup': args.warmup,
+            'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_desc(args.workload, prob),
+            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--workload', default='E', choices=sorted(CPL))
+    ap.add_argument('--no-grad', action='store_true', help='skip the gradient-evaluation leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()
