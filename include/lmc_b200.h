@@ -63,6 +63,7 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
 long lmc_op_n(const lmc_op* op);          /* total points */
 long lmc_op_grid_cells(const lmc_op* op); /* m = prod grid_sizes */
 long lmc_op_embed_bins(const lmc_op* op); /* prod of the power-of-two embedding sizes */
+int lmc_op_max_tile_points(const lmc_op* op); /* 2-D: most points staged by one scatter tile (diagnostic) */
 /* sorted position -> caller index (int32[n]); the solver keeps its state in this order */
 int lmc_op_perm(const lmc_op* op, int* perm_host);
 

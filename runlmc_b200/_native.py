@@ -46,6 +46,7 @@ SIGNATURES = {
     'lmc_op_n': (_l, [_p]),
     'lmc_op_grid_cells': (_l, [_p]),
     'lmc_op_embed_bins': (_l, [_p]),
+    'lmc_op_max_tile_points': (_i, [_p]),
     'lmc_op_perm': (_i, [_p, _p]),
     'lmc_mvm': (_i, [_p, _p, _l, _i, _p, _p]),
     'lmc_mvm_host': (_i, [_p, _p, _l, _i, _p]),

@@ -2,6 +2,7 @@
 #include "../../include/lmc_b200.h"
 #include "op.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 using namespace lmc;
@@ -46,9 +47,10 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
     const long bins = op->emb.bins, cells = op->emb.cells;
     const int D = op->D;
     if (Q > op->spec_cap) {
-        cudaFree(op->spec); cudaFree(op->B);
-        op->spec = nullptr; op->B = nullptr; op->spec_cap = 0;
+        cudaFree(op->spec); cudaFree(op->B); cudaFree(op->specL);
+        op->spec = nullptr; op->B = nullptr; op->specL = nullptr; op->spec_cap = 0;
         LMC_CHECK(cudaMalloc(&op->spec, sizeof(double) * (size_t)Q * bins));
+        LMC_CHECK(cudaMalloc(&op->specL, sizeof(double) * (size_t)Q * bins));
         LMC_CHECK(cudaMalloc(&op->B, sizeof(double) * (size_t)Q * D * D));
         op->spec_cap = Q;
     }
@@ -64,11 +66,14 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
     if (e == cudaSuccess) e = cudaMemcpy(op->noise, noise_host, sizeof(double) * D, cudaMemcpyHostToDevice);
     for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q)
         rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
+    op->fused = op->eng.fused_supported(D, Q) && getenv("LMC_NO_FUSED") == nullptr;
+    if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, Q, 0);
     if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
     cudaFree(top_dev);
     cudaFree(work);
     if (rc != 0) return rc;
     LMC_CHECK(e);
+    op->B_host.assign(B_host, B_host + (size_t)Q * D * D);
     op->Q = Q;
     return 0;
 }
@@ -76,6 +81,7 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
 long lmc_op_n(const lmc_op* op) { return op ? op->ps.n : -1; }
 long lmc_op_grid_cells(const lmc_op* op) { return op ? op->emb.cells : -1; }
 long lmc_op_embed_bins(const lmc_op* op) { return op ? op->emb.bins : -1; }
+int lmc_op_max_tile_points(const lmc_op* op) { return op ? op->ps.max_tile_pts : -1; }
 
 int lmc_op_perm(const lmc_op* op, int* perm_host) {
     LMC_REQUIRE(op && perm_host, "null argument");
@@ -136,7 +142,7 @@ int lmc_grid_mvm(lmc_op* op, const double* GIN_dev, int P, double* GOUT_dev, voi
         const int ncols = std::min(2 * cnt, P - 2 * p0);
         LMC_TRY(pack_pairs(GIN_dev + (long)2 * p0 * gm, ncols, op->D, op->emb.cells, op->G,
                            op->emb.grid_pitch, st));
-        LMC_TRY(op_grid_apply(op, op->G, cnt, op->Q, op->spec, op->B, st));
+        LMC_TRY(op_grid_block(op, op->G, cnt, st));
         LMC_TRY(unpack_pairs(op->G, op->emb.grid_pitch, GOUT_dev + (long)2 * p0 * gm, ncols, op->D,
                              op->emb.cells, st));
     }

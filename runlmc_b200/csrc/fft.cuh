@@ -221,4 +221,122 @@ __device__ __forceinline__ void fft_tile_inverse(cplx* tile, int pitch, int nl, 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Warp-per-line variant.  One warp owns one padded line in shared memory, so the
+// radix stages only need __syncwarp() between them and different lines of a CTA
+// drift apart freely (no block-wide barrier per stage).  The first forward stage
+// reads its inputs straight from global memory into registers and the last
+// inverse stage writes its outputs straight to global memory, saving one
+// shared-memory round trip each way.  Twiddles come from a per-stage table
+// tws[stage_off + (q-1)*span + o] = exp(-2 pi i o q / Ns) staged in shared memory
+// (lane-contiguous, conflict free).
+// ---------------------------------------------------------------------------
+struct StageTw {
+    int off[8];   // offset of each stage's block inside the table (stages with span == 1 have none)
+    int total;
+};
+
+static inline StageTw stage_tw_layout(int L, const FftPlan& pl) {
+    StageTw t;
+    int Ns = L, off = 0;
+    for (int s = 0; s < pl.nst; ++s) {
+        const int R = pl.radix[s], span = Ns / R;
+        t.off[s] = off;
+        if (span > 1) off += (R - 1) * span;
+        Ns /= R;
+    }
+    for (int s = pl.nst; s < 8; ++s) t.off[s] = off;
+    t.total = off;
+    return t;
+}
+
+template <int R, bool INV, bool HIN, bool HOUT, bool GLOBAL_IO>
+__device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx* tws,
+                                           const cplx* __restrict__ gsrc, cplx* gdst, int valid) {
+    const int span = Ns / R;
+    const int lane = threadIdx.x & 31;
+    for (int b = lane; b < L / R; b += 32) {
+        const int blk = b / span;
+        const int o = b - blk * span;
+        const int base = blk * Ns + o;
+        cplx x[R];
+        if (!INV) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (HIN && r >= R / 2) continue;
+                const int e = base + r * span;
+                if (GLOBAL_IO) x[r] = (e < valid) ? gsrc[e] : make_double2(0.0, 0.0);
+                else x[r] = line[pad_idx(e)];
+            }
+            Dft<R, false, HIN, false>::run(x);
+            if (span > 1) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tws[(q - 1) * span + o]);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) line[pad_idx(base + q * span)] = x[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) x[q] = line[pad_idx(base + q * span)];
+            if (span > 1) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) x[q] = cmulc(x[q], tws[(q - 1) * span + o]);
+            }
+            Dft<R, true, false, HOUT>::run(x);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (HOUT && r >= R / 2) continue;
+                const int e = base + r * span;
+                if (GLOBAL_IO) { if (e < valid) gdst[e] = x[r]; }
+                else line[pad_idx(e)] = x[r];
+            }
+        }
+    }
+}
+
+template <bool INV, bool HALF, bool GLOBAL_IO>
+__device__ __forceinline__ void warp_stage_dispatch(int R, cplx* line, int L, int Ns, const cplx* tws,
+                                                    const cplx* gsrc, cplx* gdst, int valid) {
+    if (R == 8) warp_stage<8, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+    else if (R == 4) warp_stage<4, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+    else warp_stage<2, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+}
+
+// forward transform of one line by the calling warp: global (valid prefix, rest zero) -> shared
+__device__ __forceinline__ void warp_fft_forward(const cplx* gsrc, int valid, cplx* line, int L,
+                                                 const FftPlan& pl, const StageTw& lay, const cplx* tws,
+                                                 bool half) {
+    int Ns = L;
+    for (int s = 0; s < pl.nst; ++s) {
+        const int R = pl.radix[s];
+        const cplx* t = tws + lay.off[s];
+        if (s == 0) {
+            if (half) warp_stage_dispatch<false, true, true>(R, line, L, Ns, t, gsrc, nullptr, valid);
+            else warp_stage_dispatch<false, false, true>(R, line, L, Ns, t, gsrc, nullptr, valid);
+        } else {
+            warp_stage_dispatch<false, false, false>(R, line, L, Ns, t, nullptr, nullptr, 0);
+        }
+        Ns /= R;
+        __syncwarp();
+    }
+}
+
+// inverse transform of one line by the calling warp: shared -> global (valid prefix only)
+__device__ __forceinline__ void warp_fft_inverse(cplx* line, int L, const FftPlan& pl, const StageTw& lay,
+                                                 const cplx* tws, bool half, cplx* gdst, int valid) {
+    int Ns = 1;
+    for (int s = pl.nst - 1; s >= 0; --s) {
+        const int R = pl.radix[s];
+        Ns *= R;
+        const cplx* t = tws + lay.off[s];
+        if (s == 0) {
+            if (half) warp_stage_dispatch<true, true, true>(R, line, L, Ns, t, nullptr, gdst, valid);
+            else warp_stage_dispatch<true, false, true>(R, line, L, Ns, t, nullptr, gdst, valid);
+        } else {
+            warp_stage_dispatch<true, false, false>(R, line, L, Ns, t, nullptr, nullptr, 0);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace lmc

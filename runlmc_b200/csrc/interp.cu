@@ -82,6 +82,23 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
     bool ident = true;
     for (long g = 0; g < n; ++g) ident = ident && perm[g] == (int)g;
     ps->identity = ident;
+    if (ndim == 2) {
+        // population of every (16+3) x (16+3) bin window the tiled scatter kernel stages in shared memory
+        const int T = 16, B = T + 3;
+        int worst = 0;
+        for (int d = 0; d < D; ++d)
+            for (int cx0 = 0; cx0 < ps->m[0]; cx0 += T)
+                for (int cy0 = 0; cy0 < ps->m[1]; cy0 += T) {
+                    long cnt = 0;
+                    for (int bx = cx0; bx < cx0 + B && bx < ps->nb[0]; ++bx) {
+                        const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
+                        const int hi = std::min(cy0 + B, ps->nb[1]);
+                        cnt += start[base + hi] - start[base + cy0];
+                    }
+                    worst = std::max<long>(worst, cnt);
+                }
+        ps->max_tile_pts = worst;
+    }
     std::vector<int> si(n);
     std::vector<double> su(n);
     LMC_CHECK(cudaMalloc(&ps->perm, sizeof(int) * n));
@@ -171,17 +188,25 @@ __device__ __forceinline__ bool group_active(const InterpArgs& a, int c0, int cn
 }
 
 // ---------------------------------------------------------------------------
-// 1-D scatter: one CTA owns TC = blockDim-3 consecutive cells of one output and
-// the TC+3 bins whose stencils touch them; handles PT columns (PT/2 pairs).
-// Points stream through shared memory in coalesced chunks.
+// 1-D scatter.  A CTA of 256 threads owns NBIN = 256/TPB consecutive bins of one
+// output (TPB = threads per bin, a power of two chosen from the point density so
+// that every thread has a few points) and the NBIN-3 cells whose stencils are
+// completely covered by them; it handles PT columns (PT/2 RHS pairs).  Points
+// stream through shared memory in coalesced chunks; each thread accumulates the
+// 4 per-tap partial sums of its share of its bin's points in registers, the TPB
+// partials are combined with a fixed-order shuffle tree, exchanged through
+// shared memory, and every cell adds up the (bin, tap) pairs that land on it in
+// a fixed order.  Deterministic, no atomics.
 // ---------------------------------------------------------------------------
 static const int kCap1 = 1024;
 
 template <int PT, bool PERM>
-__global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
+__global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a, int ltpb) {
     __shared__ double s_u[kCap1];
-    __shared__ double s_v[PT][kCap1];  // reused for the per-bin partial sums (needs 4*PT*256 <= PT*1024 + 1024)
-    const int TC = blockDim.x - 3;
+    __shared__ double s_v[PT][kCap1];  // reused for the per-bin partial sums (4*PT*NBIN <= PT*1024)
+    const int tpb = 1 << ltpb;
+    const int NBIN = blockDim.x >> ltpb;
+    const int TC = NBIN - 3;
     const int tile = blockIdx.x % a.tiles;
     const int d = blockIdx.x / a.tiles;
     const int col0 = blockIdx.y * PT;
@@ -190,7 +215,8 @@ __global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
     const int c0 = tile * TC;
     const int* bs = a.bin_start + (long)d * a.NB;
     const int last_bin = min(c0 + TC + 2, m + 2);
-    const int my_bin = c0 + threadIdx.x;  // bin index = i0 + 2
+    const int lbin = threadIdx.x >> ltpb, sub = threadIdx.x & (tpb - 1);
+    const int my_bin = c0 + lbin;  // bin index = i0 + 2
     const bool has_bin = my_bin <= last_bin;
     const int pbeg = bs[c0], pend = bs[last_bin + 1];
     const int my_beg = has_bin ? bs[my_bin] : 0;
@@ -212,11 +238,13 @@ __global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
             const long src = PERM ? (long)a.perm[chunk + i] : (long)(chunk + i);
 #pragma unroll
             for (int p = 0; p < PT; ++p)
-                s_v[p][i] = (col0 + p < a.ncols) ? a.in[(long)(col0 + p) * a.ld + src] * scale[p] : 0.0;
+                s_v[p][i] = (col0 + p < a.ncols) ? a.in[(long)(col0 + p) * a.ld + src] : 0.0;
         }
         __syncthreads();
         const int lo = max(my_beg, chunk) - chunk, hi = min(my_end, chunk + cnt) - chunk;
-        for (int i = lo; i < hi; ++i) {
+        // the bin's points are dealt round-robin to its TPB threads, aligned to the bin start
+        int first = lo + ((sub - (lo + chunk - my_beg)) & (tpb - 1));
+        for (int i = first; i < hi; i += tpb) {
             double w[4];
             keys_weights(s_u[i], w);
 #pragma unroll
@@ -228,18 +256,26 @@ __global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
         }
         __syncthreads();
     }
-    // exchange partial sums: sA[t][p][bin]
-    double* sA = &s_v[0][0];
-    double* sA2 = s_u;  // overflow region for PT == 1..: layout below stays within s_v + s_u
-    (void)sA2;
-    const int nthr = blockDim.x;
+    // combine the TPB partials of a bin (fixed xor tree), apply the column scale
 #pragma unroll
     for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int p = 0; p < PT; ++p) sA[(t * PT + p) * nthr + threadIdx.x] = acc[t][p];
+        for (int p = 0; p < PT; ++p) {
+            double v = acc[t][p];
+            for (int o = 1; o < tpb; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[t][p] = v * scale[p];
+        }
+    double* sA = &s_v[0][0];
+    if (sub == 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int p = 0; p < PT; ++p) sA[(t * PT + p) * NBIN + lbin] = acc[t][p];
+    }
     __syncthreads();
-    const int j = c0 + threadIdx.x;
-    if (threadIdx.x < TC && j < m) {
+    for (int c = threadIdx.x; c < TC; c += blockDim.x) {
+        const int j = c0 + c;
+        if (j >= m) break;
         double sum[PT];
 #pragma unroll
         for (int p = 0; p < PT; ++p) sum[p] = 0.0;
@@ -250,7 +286,7 @@ __global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
             for (int t = 0; t < 4; ++t) {
                 if (clampi(i0 - 1 + t, 0, m - 1) == j) {
 #pragma unroll
-                    for (int p = 0; p < PT; ++p) sum[p] += sA[(t * PT + p) * nthr + lb];
+                    for (int p = 0; p < PT; ++p) sum[p] += sA[(t * PT + p) * NBIN + lb];
                 }
             }
         }
@@ -263,22 +299,26 @@ __global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a) {
     }
 }
 
-// 1-D gather: one thread per bin keeps the 4 taps of PT columns in registers
-// and walks its points; results are staged in shared memory so the global
-// stores (and the fused  + noise * in  epilogue) are coalesced.
+// 1-D gather: the TPB threads of a bin keep the bin's 4 taps of PT columns in
+// registers and walk their share of the bin's points; results are staged in
+// shared memory so the global stores (and the fused  + noise * in  epilogue) are
+// coalesced.
 template <int PT, bool PERM>
-__global__ void __launch_bounds__(256) from_grid_1d_kernel(const InterpArgs a) {
+__global__ void __launch_bounds__(256) from_grid_1d_kernel(const InterpArgs a, int ltpb) {
     __shared__ double s_u[kCap1];
     __shared__ double s_o[PT][kCap1];
+    const int tpb = 1 << ltpb;
+    const int NBIN = blockDim.x >> ltpb;
     const int tile = blockIdx.x % a.tiles;
     const int d = blockIdx.x / a.tiles;
     const int col0 = blockIdx.y * PT;
     if (!group_active(a, col0, PT)) return;
     const int m = a.m0;
-    const int b0 = tile * blockDim.x;
+    const int b0 = tile * NBIN;
     const int* bs = a.bin_start + (long)d * a.NB;
-    const int last_bin = min(b0 + (int)blockDim.x - 1, m + 2);
-    const int my_bin = b0 + threadIdx.x;
+    const int last_bin = min(b0 + NBIN - 1, m + 2);
+    const int lbin = threadIdx.x >> ltpb, sub = threadIdx.x & (tpb - 1);
+    const int my_bin = b0 + lbin;
     const bool has_bin = my_bin <= last_bin;
     const int pbeg = bs[b0], pend = bs[last_bin + 1];
     const int my_beg = has_bin ? bs[my_bin] : 0;
@@ -305,7 +345,8 @@ __global__ void __launch_bounds__(256) from_grid_1d_kernel(const InterpArgs a) {
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_u[i] = a.u0[chunk + i];
         __syncthreads();
         const int lo = max(my_beg, chunk) - chunk, hi = min(my_end, chunk + cnt) - chunk;
-        for (int i = lo; i < hi; ++i) {
+        int first = lo + ((sub - (lo + chunk - my_beg)) & (tpb - 1));
+        for (int i = first; i < hi; i += tpb) {
             double w[4];
             keys_weights(s_u[i], w);
 #pragma unroll
@@ -470,8 +511,253 @@ __global__ void __launch_bounds__(128) from_grid_2d_kernel(const InterpArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// 2-D scatter, v2: "cell-owner gather".  A CTA owns a 16x16 tile of cells and
+// stages the points of the 19x19 surrounding bins in shared memory together
+// with their 4+4 Keys weights (computed once per point, balanced over threads,
+// reused for every RHS pair the CTA loops over).  Each thread then owns one
+// cell and sums, in fixed order, the contributions of the points in its 4x4
+// neighbouring bins: every point is visited with exactly the one (kx, ky) tap
+// that lands on the cell.  Summing 16 bins per thread evens out the Poisson
+// imbalance of sparse bins (thread-per-bin wastes ~3.4x of the lanes at 1.5
+// points per bin).  Deterministic, no atomics.
+// ---------------------------------------------------------------------------
+static const int kCap2 = 800;            // staged points per tile (host checks PointSet::max_tile_pts)
+static const int kCap2P = kCap2 + 4;     // row pitch: shifts the 4 tap rows onto different banks
+
+struct Tile2Smem {
+    double wx[4][kCap2P];
+    double wy[4][kCap2P];
+    double2 v[2][2][kCap2];  // [buffer][pair of the pass][point]: double-buffered cp.async target
+    int src[kCap2];
+    int bin[kBX][kBY + 1];   // local offsets of every bin of the window (+ end of row)
+    int row_beg[kBX];        // global sorted index of the first point of each bin row
+    int row_off[kBX + 1];    // local prefix
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+template <bool PERM>
+__global__ void __launch_bounds__(256, 2) to_grid_2d_v2_kernel(const InterpArgs a, int pairs_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    Tile2Smem& s = *reinterpret_cast<Tile2Smem*>(smem_raw2);
+    const int tile = blockIdx.x % a.tiles;
+    const int d = blockIdx.x / a.tiles;
+    const int pair0 = blockIdx.y * pairs_per_cta;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    const int mx = a.m0, my = a.m1;
+    const int tx = tile / a.tiles1, ty = tile % a.tiles1;
+    const int cx0 = tx * kTX, cy0 = ty * kTY;
+    const int* bs = a.bin_start + (long)d * a.NB;
+    const int tid = threadIdx.x;
+
+    // ---- window geometry ----
+    if (tid < kBX) {
+        const int bx = cx0 + tid;
+        int beg = 0, end = 0;
+        if (bx <= mx + 2) {
+            const int by_hi = min(cy0 + kBY, my + 3);
+            beg = bs[(long)bx * a.nb1 + cy0];
+            end = bs[(long)bx * a.nb1 + by_hi];
+        }
+        s.row_beg[tid] = beg;
+        s.row_off[tid + 1] = end - beg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s.row_off[0] = 0;
+        for (int r = 0; r < kBX; ++r) s.row_off[r + 1] += s.row_off[r];
+    }
+    __syncthreads();
+    for (int i = tid; i < kBX * (kBY + 1); i += blockDim.x) {
+        const int r = i / (kBY + 1), c = i % (kBY + 1);
+        const int bx = cx0 + r;
+        int off = s.row_off[r + 1];
+        if (bx <= mx + 2) {
+            const int by = min(cy0 + c, my + 3);
+            off = s.row_off[r] + (bs[(long)bx * a.nb1 + by] - s.row_beg[r]);
+        }
+        s.bin[r][c] = off;
+    }
+    const int npts = s.row_off[kBX];
+    const int npass = (min(pairs_per_cta, npairs_tot - pair0) + 1) >> 1;
+
+    // stage the RHS values of pass `ps` (two pairs = four columns) with cp.async; columns past the
+    // end of the block are zero-filled by ordinary stores
+    auto stage = [&](int ps, int buf) {
+        const int pair = pair0 + 2 * ps;
+        for (int i = tid; i < npts; i += blockDim.x) {
+            const long src = s.src[i];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int c = 2 * pair + h;
+                double* dst = reinterpret_cast<double*>(&s.v[buf][h >> 1][i]) + (h & 1);
+                if (c < a.ncols && (h < 2 || 2 * ps + 1 < pairs_per_cta)) cp_async8(dst, a.in + (long)c * a.ld + src);
+                else *dst = 0.0;
+            }
+        }
+        cp_async_commit();
+    };
+
+    // ---- per-point weights (once per CTA) ----
+    for (int i = tid; i < npts; i += blockDim.x) {
+        int r = 0;
+        while (i >= s.row_off[r + 1]) ++r;
+        const int g = s.row_beg[r] + (i - s.row_off[r]);
+        double wx[4], wy[4];
+        keys_weights(a.u0[g], wx);
+        keys_weights(a.u1[g], wy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s.wx[k][i] = wx[k]; s.wy[k][i] = wy[k]; }
+        s.src[i] = PERM ? a.perm[g] : g;
+    }
+    __syncthreads();
+    if (npass > 0) stage(0, 0);
+
+    const int lcx = tid / kTY, lcy = tid % kTY;
+    const int jx = cx0 + lcx, jy = cy0 + lcy;
+    const bool in_grid = jx < mx && jy < my;
+    const bool interior = jx >= 1 && jx <= mx - 2 && jy >= 1 && jy <= my - 2;
+
+    for (int ps = 0; ps < npass; ++ps) {
+        const int buf = ps & 1;
+        const int pair = pair0 + 2 * ps;
+        const bool second = (2 * ps + 1 < pairs_per_cta) && (pair + 1 < npairs_tot);
+        cp_async_wait_all();
+        __syncthreads();                       // pass ps is staged; every thread finished pass ps-1
+        if (ps + 1 < npass) stage(ps + 1, buf ^ 1);   // overlaps with the gather below
+        if (!in_grid || !group_active(a, 2 * pair, second ? 4 : 2)) continue;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double2* va_ = s.v[buf][0];
+        const double2* vb_ = s.v[buf][1];
+        if (interior) {
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) {
+                const int r = lcx + aa;          // bin row i0x = jx - 2 + aa  ->  tap kx = 3 - aa
+                const double* wxr = s.wx[3 - aa];
+                // the 4 bins (r, lcy..lcy+3) are one contiguous run of points; ky from the bin a point is in
+                const int b0 = s.bin[r][lcy], b1 = s.bin[r][lcy + 1], b2 = s.bin[r][lcy + 2];
+                const int b3 = s.bin[r][lcy + 3], b4 = s.bin[r][lcy + 4];
+                for (int i = b0; i < b4; ++i) {
+                    const int ky = 3 - ((i >= b1) + (i >= b2) + (i >= b3));
+                    const double w = wxr[i] * s.wy[ky][i];
+                    const double2 va = va_[i], vb = vb_[i];
+                    acc[0] = fma(w, va.x, acc[0]);
+                    acc[1] = fma(w, va.y, acc[1]);
+                    acc[2] = fma(w, vb.x, acc[2]);
+                    acc[3] = fma(w, vb.y, acc[3]);
+                }
+            }
+        } else {
+            // grid-edge cell: clamped taps of several bins / several taps of one bin land here
+            const int xlo = max(jx - 2, -2), xhi = min(jx + 1, mx);
+            const int ylo = max(jy - 2, -2), yhi = min(jy + 1, my);
+            for (int ix = xlo; ix <= xhi; ++ix) {
+                const int r = ix + 2 - cx0;
+                for (int iy = ylo; iy <= yhi; ++iy) {
+                    const int c = iy + 2 - cy0;
+                    for (int i = s.bin[r][c]; i < s.bin[r][c + 1]; ++i) {
+                        double wxs = 0.0, wys = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (clampi(ix - 1 + k, 0, mx - 1) == jx) wxs += s.wx[k][i];
+                            if (clampi(iy - 1 + k, 0, my - 1) == jy) wys += s.wy[k][i];
+                        }
+                        const double w = wxs * wys;
+                        const double2 va = va_[i], vb = vb_[i];
+                        acc[0] = fma(w, va.x, acc[0]);
+                        acc[1] = fma(w, va.y, acc[1]);
+                        acc[2] = fma(w, vb.x, acc[2]);
+                        acc[3] = fma(w, vb.y, acc[3]);
+                    }
+                }
+            }
+        }
+        if (a.in_scale) {   // W^T (v s) = s W^T v: the column scale is applied to the sums
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int c = 2 * pair + h;
+                if (c < a.ncols) acc[h] *= a.in_scale[c];
+            }
+        }
+        const long cell = (long)jx * my + jy;
+        a.G[((long)pair * a.D + d) * a.grid_pitch + cell] = make_double2(acc[0], acc[1]);
+        if (second) a.G[((long)(pair + 1) * a.D + d) * a.grid_pitch + cell] = make_double2(acc[2], acc[3]);
+    }
+}
+
+// 2-D gather, v2: one thread per point loops over the RHS pairs of its group, so the
+// 4+4 weights and the 16 clamped cell offsets are computed once per point.
+template <bool PERM>
+__global__ void __launch_bounds__(128) from_grid_2d_v2_kernel(const InterpArgs a, int pairs_per_cta) {
+    const int d = blockIdx.y;
+    const long i = a.out_start[d] + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.out_start[d + 1]) return;
+    const int mx = a.m0, my = a.m1;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    double wx[4], wy[4];
+    keys_weights(a.u0[i], wx);
+    keys_weights(a.u1[i], wy);
+    const int ix0 = a.i00[i] - 1, iy0 = a.i01[i] - 1;
+    int cy[4];
+    long row[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cy[j] = clampi(iy0 + j, 0, my - 1);
+        row[j] = (long)clampi(ix0 + j, 0, mx - 1) * my;
+    }
+    const long dst = PERM ? (long)a.perm[i] : i;
+    const double nz = a.noise ? a.noise[d] : 0.0;
+    const int pair0 = blockIdx.z * pairs_per_cta;
+    for (int pp = 0; pp < pairs_per_cta; ++pp) {
+        const int pair = pair0 + pp;
+        if (pair >= npairs_tot) break;
+        const int col0 = 2 * pair;
+        if (!group_active(a, col0, 2)) continue;
+        const cplx* g = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
+        double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const cplx v = __ldg(&g[row[k] + cy[j]]);
+                r0 = fma(wy[j], v.x, r0);
+                r1 = fma(wy[j], v.y, r1);
+            }
+            o0 = fma(wx[k], r0, o0);
+            o1 = fma(wx[k], r1, o1);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int c = col0 + p;
+            if (c >= a.ncols) continue;
+            if (a.active && !a.active[c]) continue;
+            double o = p ? o1 : o0;
+            if (a.noise) {
+                const double sc = a.in_scale ? a.in_scale[c] : 1.0;
+                o = fma(nz, a.in[(long)c * a.ld + dst] * sc, o);
+            }
+            a.out[(long)c * a.ld + dst] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
+// threads per bin of the 1-D kernels: keep ~4 points per thread at the average density
+static int threads_per_bin_log2(const PointSet& ps) {
+    const double density = (double)ps.n / ((double)ps.D * ps.m[0]);
+    int l = 0;
+    while (l < 5 && density > 4.0 * (1 << l)) ++l;
+    return l;
+}
+
 static InterpArgs make_args(const PointSet& ps, const ColumnView& cv) {
     InterpArgs a = {};
     a.u0 = ps.u[0]; a.u1 = ps.u[1];
@@ -494,15 +780,38 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     ProfScope prof(PROF_TO_GRID, st);
     const bool perm = !(cv.sorted_io || ps.identity);
     if (ps.ndim == 1) {
-        const int threads = 256, TC = threads - 3, PT = 4;
+        const int threads = 256, PT = 4;
+        const int ltpb = threads_per_bin_log2(ps);
+        const int TC = (threads >> ltpb) - 3;
         a.tiles = ceil_div(ps.m[0], TC);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(cv.ncols, PT));
-        if (perm) to_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a);
-        else to_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a);
+        if (perm) to_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a, ltpb);
+        else to_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a, ltpb);
     } else {
         a.tiles1 = ceil_div(ps.m[1], kTY);
         a.tiles = ceil_div(ps.m[0], kTX) * a.tiles1;
-        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)((cv.ncols + 1) / 2));
+        const int npairs = (cv.ncols + 1) / 2;
+        if (ps.max_tile_pts <= kCap2) {
+            static bool attr2 = false;
+            if (!attr2) {
+                LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_v2_kernel<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)));
+                LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_v2_kernel<false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)));
+                attr2 = true;
+            }
+            // enough CTAs to fill the machine a few times over, as many pairs per CTA as that allows
+            const long ctas1 = (long)a.tiles * ps.D;
+            int ppc = (int)std::max<long>(1, std::min<long>(8, (ctas1 * npairs) / (148L * 3 * 4)));
+            ppc = std::min(ppc, npairs);
+            dim3 grid2((unsigned)ctas1, (unsigned)ceil_div(npairs, ppc));
+            if (perm) to_grid_2d_v2_kernel<true><<<grid2, 256, sizeof(Tile2Smem), st>>>(a, ppc);
+            else to_grid_2d_v2_kernel<false><<<grid2, 256, sizeof(Tile2Smem), st>>>(a, ppc);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+            return 0;
+        }
+        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)npairs);
         const size_t smem = sizeof(double) * 32 * kBX * kBY;
         static bool attr = false;
         if (!attr) {
@@ -530,17 +839,22 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
     const bool perm = !(cv.sorted_io || ps.identity);
     if (ps.ndim == 1) {
         const int threads = 256, PT = 4;
-        a.tiles = ceil_div(ps.m[0] + 3, threads);
+        const int ltpb = threads_per_bin_log2(ps);
+        a.tiles = ceil_div(ps.m[0] + 3, threads >> ltpb);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(cv.ncols, PT));
-        if (perm) from_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a);
-        else from_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a);
+        if (perm) from_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a, ltpb);
+        else from_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a, ltpb);
     } else {
         long maxlen = 0;
         for (int d = 0; d < ps.D; ++d) maxlen = std::max(maxlen, ps.out_start[d + 1] - ps.out_start[d]);
         if (maxlen == 0) return 0;
-        dim3 grid((unsigned)ceil_div(maxlen, 128), (unsigned)ps.D, (unsigned)((cv.ncols + 1) / 2));
-        if (perm) from_grid_2d_kernel<true><<<grid, 128, 0, st>>>(a);
-        else from_grid_2d_kernel<false><<<grid, 128, 0, st>>>(a);
+        const int npairs = (cv.ncols + 1) / 2;
+        const long ctas1 = (long)ceil_div(maxlen, 128) * ps.D;
+        int ppc = (int)std::max<long>(1, std::min<long>(8, (ctas1 * npairs) / (148L * 16 * 4)));
+        ppc = std::min(ppc, npairs);
+        dim3 grid((unsigned)ceil_div(maxlen, 128), (unsigned)ps.D, (unsigned)ceil_div(npairs, ppc));
+        if (perm) from_grid_2d_v2_kernel<true><<<grid, 128, 0, st>>>(a, ppc);
+        else from_grid_2d_v2_kernel<false><<<grid, 128, 0, st>>>(a, ppc);
     }
     count_launch();
     LMC_CHECK(cudaGetLastError());

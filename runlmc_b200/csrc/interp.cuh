@@ -14,6 +14,7 @@ struct PointSet {
     long NB = 0;          // bins per output
     long grid_pitch = 0;  // cells allocated per (pair, output) slab
     bool identity = false;  // sorted order == caller's order
+    int max_tile_pts = 0;   // 2-D: largest point count of a 16x16-cell tile incl. its 3-bin halo
     int* perm = nullptr;     // [n] sorted position -> caller's index
     double* u[2] = {nullptr, nullptr};  // [n] fractional offsets (sorted order)
     int* i0[2] = {nullptr, nullptr};    // [n] clamped base index (sorted order)

@@ -44,7 +44,14 @@ int op_ensure_workspace(lmc_op* op) {
     int tile = (int)std::max<size_t>(1, kSpectrumTileBytes / per_pair);
     tile = std::min(tile, 256);
     op->tile_pairs = tile;
-    const size_t gbytes = sizeof(cplx) * (size_t)tile * op->D * op->emb.grid_pitch;
+    const size_t fpp = sizeof(cplx) * op->eng.fused_elems_per_pair(op->D);
+    op->fused_tile_pairs = fpp ? (int)std::max<size_t>(1, (per_pair * tile) / fpp) : 256;
+    // interpolation runs over a wider block of pairs than the spectral stage: the grid slabs are
+    // small (cells << bins) and the scatter/gather kernels amortise their per-point weights over pairs
+    const size_t per_pair_g = sizeof(cplx) * (size_t)op->D * op->emb.grid_pitch;
+    int gp = (int)std::max<size_t>(tile, std::min<size_t>(64, (1ull << 30) / per_pair_g));
+    op->g_pairs = gp;
+    const size_t gbytes = per_pair_g * gp;
     LMC_CHECK(cudaMalloc(&op->G, gbytes));
     LMC_CHECK(cudaMemset(op->G, 0, gbytes));
     LMC_CHECK(cudaMalloc(&op->S, per_pair * tile));
@@ -60,12 +67,27 @@ int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, co
     return 0;
 }
 
+// (sum_q B_q (x) T_q) applied in place to `cnt` RHS pairs of grid slabs, in L2-sized sub-tiles
+int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st) {
+    const size_t slab = (size_t)op->D * op->emb.grid_pitch;
+    const int step = op->fused ? op->fused_tile_pairs : op->tile_pairs;
+    for (int q0 = 0; q0 < cnt; q0 += step) {
+        const int qc = std::min(step, cnt - q0);
+        cplx* g = G + (size_t)q0 * slab;
+        if (op->fused)
+            LMC_TRY(op->eng.apply_fused(g, op->S, qc, op->D, op->Q, op->specL, op->B_host.data(), st));
+        else
+            LMC_TRY(op_grid_apply(op, g, qc, op->Q, op->spec, op->B, st));
+    }
+    return 0;
+}
+
 int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
     LMC_TRY(op_ensure_workspace(op));
     const int npairs = (cv.ncols + 1) / 2;
-    for (int p0 = 0; p0 < npairs; p0 += op->tile_pairs) {
-        const int cnt = std::min(op->tile_pairs, npairs - p0);
+    for (int p0 = 0; p0 < npairs; p0 += op->g_pairs) {
+        const int cnt = std::min(op->g_pairs, npairs - p0);
         ColumnView t = cv;
         const int c0 = 2 * p0;
         t.in = cv.in + (long)c0 * cv.ld;
@@ -74,7 +96,7 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
         t.in_scale = cv.in_scale ? cv.in_scale + c0 : nullptr;
         t.active = cv.active ? cv.active + c0 : nullptr;
         LMC_TRY(to_grid(op->ps, t, op->G, st));
-        LMC_TRY(op_grid_apply(op, op->G, cnt, op->Q, op->spec, op->B, st));
+        LMC_TRY(op_grid_block(op, op->G, cnt, st));
         LMC_TRY(from_grid(op->ps, t, op->G, op->noise, st));
     }
     return 0;
@@ -85,6 +107,7 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
 lmc_op::~lmc_op() {
     lmc::free_points(&ps);
     cudaFree(spec);
+    cudaFree(specL);
     cudaFree(B);
     cudaFree(noise);
     cudaFree(G);

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "interp.cuh"
 #include "spectral.cuh"
+#include <vector>
 
 struct lmc_op {
     int D = 0, ndim = 0, Q = 0;
@@ -10,12 +11,17 @@ struct lmc_op {
     lmc::SpectralEngine eng;
     lmc::PointSet ps;
     double* spec = nullptr;   // [Q][bins] real circulant spectra / bins (digit-reversed layout)
+    double* specL = nullptr;  // [Q][line][pos] line-major copy for the fused spectral kernel
+    std::vector<double> B_host;
+    bool fused = false;       // fused spectral path usable for this geometry / D / Q
+    int fused_tile_pairs = 0;
     double* B = nullptr;      // [Q][D][D]
     double* noise = nullptr;  // [D]
     int spec_cap = 0;         // allocated Q
     // grid-stage workspace for `tile_pairs` RHS pairs
-    cplx* G = nullptr;        // [tile_pairs][D][grid_pitch]
-    cplx* S = nullptr;        // [tile_pairs][D][bins]
+    cplx* G = nullptr;        // [g_pairs][D][grid_pitch]  grid-side vectors of a block of RHS pairs
+    cplx* S = nullptr;        // [tile_pairs][D][bins]     spectra of one L2-sized sub-tile of pairs
+    int g_pairs = 0;
     int tile_pairs = 0;
     ~lmc_op();
 };
@@ -38,6 +44,7 @@ int op_ensure_workspace(lmc_op* op);
 int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st);
 // same without the noise term and with explicit spectra / mixing matrices
 // (used by the gradient stage); spec/B device pointers, Q kernels
+int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st);
 int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, const double* B,
                   cudaStream_t st);
 

@@ -382,11 +382,218 @@ __global__ void mix_generic_kernel(const cplx* __restrict__ Sin, cplx* Sout, lon
 }
 
 // ---------------------------------------------------------------------------
+// Fused spectral kernels
+// ---------------------------------------------------------------------------
+// 2-D row pass that also transposes: rows of G (y contiguous) <-> S_T[slab][ky][x] (x contiguous), so
+// the column transforms of the fused kernel below read/write contiguous lines.  NR rows per CTA give
+// 16*NR-byte contiguous chunks on the transposed side.
+struct RowsTArgs {
+    const cplx* G_in;   // forward source
+    cplx* G_out;        // inverse destination
+    cplx* ST;
+    long g_slab, st_slab;   // elements per slab
+    int mx, my, mty, xpitch;
+    const cplx* stage_tw;   // per-stage twiddle tables for line length mty
+    int tw_total;
+    StageTw lay;
+    FftPlan plan;
+    int pitch, half, nr, lnr;
+};
+
+template <bool INV>
+__global__ void __launch_bounds__(256) fft_rows_T_kernel(const RowsTArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tws = reinterpret_cast<cplx*>(smem_raw);
+    cplx* tile = tws + a.tw_total;
+    const int L = a.mty, nr = a.nr, pitch = a.pitch;
+    const int x0 = blockIdx.x * nr;
+    const long slab = blockIdx.y;
+    cplx* st = a.ST + slab * a.st_slab;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < a.tw_total; i += blockDim.x) tws[i] = a.stage_tw[i];
+    __syncthreads();
+    if (!INV) {
+        const cplx* g = a.G_in + slab * a.g_slab;
+        for (int l = warp; l < nr; l += nwarps) {
+            const int valid = (x0 + l < a.mx) ? a.my : 0;   // rows past the grid are zero lines
+            warp_fft_forward(g + (long)(x0 + l) * a.my, valid, tile + l * pitch, L, a.plan, a.lay, tws,
+                             a.half != 0);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < L * nr; idx += blockDim.x) {
+            const int e = idx >> a.lnr, l = idx & (nr - 1);
+            st[(long)e * a.xpitch + x0 + l] = tile[l * pitch + pad_idx(e)];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < L * nr; idx += blockDim.x) {
+            const int e = idx >> a.lnr, l = idx & (nr - 1);
+            tile[l * pitch + pad_idx(e)] = st[(long)e * a.xpitch + x0 + l];
+        }
+        __syncthreads();
+        cplx* g = a.G_out + slab * a.g_slab;
+        for (int l = warp; l < nr; l += nwarps) {
+            const int valid = (x0 + l < a.mx) ? a.my : 0;
+            warp_fft_inverse(tile + l * pitch, L, a.plan, a.lay, tws, a.half != 0,
+                             g + (long)(x0 + l) * a.my, valid);
+        }
+    }
+}
+
+// Forward transform of the D lines of one RHS pair, per-bin coregionalisation mix, inverse
+// transform -- all in shared memory, in place on global memory.  The mixing matrices travel as
+// kernel parameters so they are constant-bank operands of the DFMAs.
+template <int D>
+struct MixB {
+    double b[8][D][D];
+};
+
+struct FusedArgs {
+    cplx* data;
+    long slab_stride, line_stride;
+    int n_lines, L, valid, lpc;   // lines per slab, line length, valid prefix, line-sets per CTA
+    int Q;
+    const double* specL;          // [Q][n_lines][L]
+    const cplx* stage_tw;         // per-stage twiddle tables (global), layout `lay`
+    int tw_total;
+    StageTw lay;
+    FftPlan plan;
+    int pitch, half;
+};
+
+template <int D>
+__global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, const MixB<D> mb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tws = reinterpret_cast<cplx*>(smem_raw);            // per-stage twiddle tables
+    cplx* tile = tws + a.tw_total;                            // [lpc*D][pitch]
+    const int L = a.L, pitch = a.pitch, lpc = a.lpc;
+    const int lL = 31 - __clz(L);
+    const int line0 = blockIdx.x * lpc;
+    const long pair = blockIdx.y;
+    cplx* base = a.data + pair * D * a.slab_stride;
+    const int nl = lpc * D;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < a.tw_total; i += blockDim.x) tws[i] = a.stage_tw[i];
+    __syncthreads();
+    for (int li = warp; li < nl; li += nwarps) {
+        const int ll = li / D, d = li - ll * D;
+        if (line0 + ll >= a.n_lines) continue;
+        const cplx* g = base + d * a.slab_stride + (long)(line0 + ll) * a.line_stride;
+        warp_fft_forward(g, a.valid, tile + li * pitch, L, a.plan, a.lay, tws, a.half != 0);
+    }
+    __syncthreads();
+    // ---- mix:  y[dp] = sum_d (sum_q f_q B_q[dp][d]) x[d]  at every bin of every line-set ----
+    for (int w = threadIdx.x; w < lpc * L; w += blockDim.x) {
+        const int ll = w >> lL, p = w & (L - 1);
+        if (line0 + ll >= a.n_lines) continue;
+        cplx* col = tile + (ll * D) * pitch + pad_idx(p);
+        cplx x[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = col[d * pitch];
+        double f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            f[q] = (q < a.Q) ? __ldg(&a.specL[((long)q * a.n_lines + line0 + ll) * L + p]) : 0.0;
+#pragma unroll
+        for (int dp = 0; dp < D; ++dp) {
+            double m[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) m[d] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < a.Q) {   // warp-uniform
+#pragma unroll
+                    for (int d = 0; d < D; ++d) m[d] = fma(f[q], mb.b[q][dp][d], m[d]);
+                }
+            }
+            double yr = 0.0, yi = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                yr = fma(m[d], x[d].x, yr);
+                yi = fma(m[d], x[d].y, yi);
+            }
+            col[dp * pitch] = make_double2(yr, yi);
+        }
+    }
+    __syncthreads();
+    for (int li = warp; li < nl; li += nwarps) {
+        const int ll = li / D, d = li - ll * D;
+        if (line0 + ll >= a.n_lines) continue;
+        cplx* g = base + d * a.slab_stride + (long)(line0 + ll) * a.line_stride;
+        warp_fft_inverse(tile + li * pitch, L, a.plan, a.lay, tws, a.half != 0, g, a.valid);
+    }
+}
+
+__global__ void transpose2_kernel(const double* __restrict__ in, double* out, int R, int C) {
+    __shared__ double t[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (r0 + j < R && c0 + threadIdx.x < C) t[j][threadIdx.x] = in[(long)(r0 + j) * C + c0 + threadIdx.x];
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y)
+        if (c0 + j < C && r0 + threadIdx.x < R) out[(long)(c0 + j) * R + r0 + threadIdx.x] = t[threadIdx.x][j];
+}
+
+// tab[off_s + (q-1)*span + o] = exp(-2 pi i o q / Ns) for every stage with span > 1
+__global__ void stage_twiddle_kernel(cplx* tab, int L, FftPlan pl, StageTw lay) {
+    int Ns = L;
+    for (int s = 0; s < pl.nst; ++s) {
+        const int R = pl.radix[s], span = Ns / R;
+        if (span > 1) {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (R - 1) * span; i += gridDim.x * blockDim.x) {
+                const int q = i / span + 1, o = i % span;
+                double sn, cs;
+                sincospi(-2.0 * (double)(o * q) / (double)Ns, &sn, &cs);
+                tab[lay.off[s] + i] = make_double2(cs, sn);
+            }
+        }
+        Ns /= R;
+    }
+}
+
+static const size_t kFusedSmemMax = 200 * 1024;
+
+template <int D>
+static int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const double* B_host, int npairs,
+                              cudaStream_t st) {
+    static MixB<D> mb;   // zero-initialised; only the first Q blocks are read
+    for (int q = 0; q < a.Q; ++q)
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) mb.b[q][i][j] = B_host[((size_t)q * D + i) * D + j];
+    a.plan = make_plan(a.L);
+    a.lay = stage_tw_layout(a.L, a.plan);
+    a.tw_total = a.lay.total;
+    a.stage_tw = stage_tw;
+    a.pitch = line_pitch(a.L);
+    a.half = (a.L >= 2 && a.valid <= a.L / 2) ? 1 : 0;
+    const size_t per_set = (size_t)D * a.pitch * sizeof(cplx);
+    int lpc = (int)std::max<size_t>(1, std::min<size_t>(48 * 1024 / per_set, (size_t)(4096 / (D * a.L) + 1)));
+    lpc = std::max(1, std::min(lpc, a.n_lines));
+    a.lpc = lpc;
+    const size_t smem = per_set * lpc + sizeof(cplx) * (size_t)a.tw_total;
+    LMC_REQUIRE(smem <= kFusedSmemMax, "fused spectral tile does not fit shared memory");
+    static bool attr = false;
+    if (!attr) {
+        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kFusedSmemMax));
+        attr = true;
+    }
+    const int threads = 32 * std::max(2, std::min(10, lpc * D));   // one warp per line, up to 10 warps
+    dim3 grid((unsigned)ceil_div(a.n_lines, lpc), (unsigned)npairs);
+    ProfScope prof(PROF_MIX, st);
+    fused_lines_kernel<D><<<grid, threads, smem, st>>>(a, mb);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // SpectralEngine
 // ---------------------------------------------------------------------------
 SpectralEngine::~SpectralEngine() {
     for (int p = 0; p < 3; ++p)
         if (tw_[p]) cudaFree(tw_[p]);
+    if (stage_tw_) cudaFree(stage_tw_);
+    if (stage_tw_rows_) cudaFree(stage_tw_rows_);
 }
 
 int SpectralEngine::init(const Embedding& emb) {
@@ -593,6 +800,156 @@ int SpectralEngine::inverse(cplx* S, cplx* G, int nslab, cudaStream_t st) {
     crop3_kernel<<<ceil_div(total, 256), 256, 0, st>>>(S, G, e.grid_pitch, e, nslab);
     count_launch();
     LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+bool SpectralEngine::fused_supported(int D, int Q) const {
+    if (D > 16 || Q > 8 || emb_.ndim > 2) return false;
+    const int L = emb_.ndim == 2 ? emb_.mt[0] : emb_.L2;
+    return (size_t)D * line_pitch(L) * sizeof(cplx) + sizeof(cplx) * (size_t)L <= kFusedSmemMax;
+}
+
+size_t SpectralEngine::fused_elems_per_pair(int D) const {
+    if (emb_.ndim == 2) return (size_t)D * emb_.mt[1] * (size_t)(ceil_div(emb_.m[0], 8) * 8);
+    if (emb_.L1 > 1) return (size_t)D * emb_.bins;
+    return 0;   // 1-D short lines are transformed in place in the grid slabs
+}
+
+int SpectralEngine::spectrum_lines(const double* spec, double* specL, int Q, cudaStream_t st) {
+    for (int q = 0; q < Q; ++q) {
+        const double* in = spec + (size_t)q * emb_.bins;
+        double* out = specL + (size_t)q * emb_.bins;
+        if (emb_.ndim == 2) {
+            dim3 grid((unsigned)ceil_div(emb_.mt[1], 32), (unsigned)ceil_div(emb_.mt[0], 32));
+            transpose2_kernel<<<grid, dim3(32, 8), 0, st>>>(in, out, emb_.mt[0], emb_.mt[1]);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        } else {
+            LMC_CHECK(cudaMemcpyAsync(out, in, sizeof(double) * emb_.bins, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return 0;
+}
+
+int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL,
+                                const double* B_host, cudaStream_t st) {
+    if (npairs == 0) return 0;
+    const Embedding& e = emb_;
+    FusedArgs f = {};
+    f.Q = Q;
+    f.specL = specL;
+    // stage twiddle table of the fused kernel's line length (built on first use)
+    const int Lf = e.ndim == 2 ? e.mt[0] : e.L2;
+    if (!stage_tw_) {
+        const FftPlan pl = make_plan(Lf);
+        const StageTw lay = stage_tw_layout(Lf, pl);
+        LMC_CHECK(cudaMalloc(&stage_tw_, sizeof(cplx) * (size_t)std::max(lay.total, 1)));
+        stage_twiddle_kernel<<<8, 256, 0, st>>>(stage_tw_, Lf, pl, lay);
+        count_launch();
+        LMC_CHECK(cudaGetLastError());
+    }
+    const cplx* stw = stage_tw_;
+    if (e.ndim == 2) {
+        const int xpitch = ceil_div(e.m[0], 8) * 8;
+        RowsTArgs r = {};
+        r.G_in = G; r.G_out = G; r.ST = S;
+        r.g_slab = e.grid_pitch; r.st_slab = (long)e.mt[1] * xpitch;
+        r.mx = e.m[0]; r.my = e.m[1]; r.mty = e.mt[1]; r.xpitch = xpitch;
+        r.plan = make_plan(e.mt[1]);
+        r.lay = stage_tw_layout(e.mt[1], r.plan);
+        r.tw_total = r.lay.total;
+        if (!stage_tw_rows_) {
+            LMC_CHECK(cudaMalloc(&stage_tw_rows_, sizeof(cplx) * (size_t)std::max(r.lay.total, 1)));
+            stage_twiddle_kernel<<<8, 256, 0, st>>>(stage_tw_rows_, e.mt[1], r.plan, r.lay);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        }
+        r.stage_tw = stage_tw_rows_;
+        r.pitch = line_pitch(e.mt[1]);
+        r.half = 1;   // mty >= 2 my always
+        r.nr = 8; r.lnr = 3;
+        const size_t smem = ((size_t)r.nr * r.pitch + r.tw_total) * sizeof(cplx);
+        LMC_REQUIRE(smem <= kFusedSmemMax, "row tile does not fit shared memory");
+        static bool attr = false;
+        if (!attr) {
+            LMC_CHECK(cudaFuncSetAttribute(fft_rows_T_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kFusedSmemMax));
+            LMC_CHECK(cudaFuncSetAttribute(fft_rows_T_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kFusedSmemMax));
+            attr = true;
+        }
+        const int threads = 256;   // one warp per row
+        dim3 grid((unsigned)(xpitch / r.nr), (unsigned)(npairs * D));
+        {
+            ProfScope prof(PROF_FFT_FWD_CONTIG, st);
+            fft_rows_T_kernel<false><<<grid, threads, smem, st>>>(r);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        }
+        f.data = S;
+        f.slab_stride = r.st_slab; f.line_stride = xpitch;
+        f.n_lines = e.mt[1]; f.L = e.mt[0]; f.valid = e.m[0];
+        int rc = 1;
+        switch (D) {
+#define LMC_FUSED_CASE(DD) case DD: rc = launch_fused_lines<DD>(f, stw, B_host, npairs, st); break;
+            LMC_FUSED_CASE(1) LMC_FUSED_CASE(2) LMC_FUSED_CASE(3) LMC_FUSED_CASE(4) LMC_FUSED_CASE(5)
+            LMC_FUSED_CASE(6) LMC_FUSED_CASE(7) LMC_FUSED_CASE(8) LMC_FUSED_CASE(9) LMC_FUSED_CASE(10)
+            LMC_FUSED_CASE(11) LMC_FUSED_CASE(12) LMC_FUSED_CASE(13) LMC_FUSED_CASE(14) LMC_FUSED_CASE(15)
+            LMC_FUSED_CASE(16)
+        }
+        LMC_TRY(rc);
+        {
+            ProfScope prof(PROF_FFT_INV_CONTIG, st);
+            fft_rows_T_kernel<true><<<grid, threads, smem, st>>>(r);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        }
+        return 0;
+    }
+    // ---- 1-D ----
+    if (e.L1 == 1) {
+        f.data = G;
+        f.slab_stride = e.grid_pitch; f.line_stride = 0;
+        f.n_lines = 1; f.L = e.mt[0]; f.valid = e.m[0];
+    } else {
+        // four-step: strided pass over j1 with the twist, fused inner transforms over j2, and back
+        PassArgs a = {};
+        a.src_flat_valid = a.dst_flat_valid = -1;
+        a.n_batch = npairs * D;
+        a.src = G; a.dst = S;
+        a.src_bs = e.grid_pitch; a.src_os = 0; a.src_es = e.L2;
+        a.dst_bs = e.bins; a.dst_os = 0; a.dst_es = e.L2;
+        a.L = e.L1; a.n_inner = e.L2; a.n_outer = 1;
+        a.valid_in = ceil_div(e.m[0], e.L2); a.src_flat_valid = e.m[0];
+        a.valid_out = a.L;
+        a.tw = tw_[0]; a.tw_n = tw_n_[0]; a.twist = 1;
+        LMC_TRY(launch_pass(a, true, false, st));
+        f.data = S;
+        f.slab_stride = e.bins; f.line_stride = e.L2;
+        f.n_lines = e.L1; f.L = e.L2; f.valid = e.L2;
+    }
+    int rc = 1;
+    switch (D) {
+        LMC_FUSED_CASE(1) LMC_FUSED_CASE(2) LMC_FUSED_CASE(3) LMC_FUSED_CASE(4) LMC_FUSED_CASE(5)
+        LMC_FUSED_CASE(6) LMC_FUSED_CASE(7) LMC_FUSED_CASE(8) LMC_FUSED_CASE(9) LMC_FUSED_CASE(10)
+        LMC_FUSED_CASE(11) LMC_FUSED_CASE(12) LMC_FUSED_CASE(13) LMC_FUSED_CASE(14) LMC_FUSED_CASE(15)
+        LMC_FUSED_CASE(16)
+#undef LMC_FUSED_CASE
+    }
+    LMC_TRY(rc);
+    if (e.L1 > 1) {
+        PassArgs a = {};
+        a.src_flat_valid = a.dst_flat_valid = -1;
+        a.n_batch = npairs * D;
+        a.src = S; a.dst = G;
+        a.src_bs = e.bins; a.src_os = 0; a.src_es = e.L2;
+        a.dst_bs = e.grid_pitch; a.dst_os = 0; a.dst_es = e.L2;
+        a.L = e.L1; a.n_inner = e.L2; a.n_outer = 1;
+        a.valid_in = a.L; a.valid_out = ceil_div(e.m[0], e.L2);
+        a.dst_flat_valid = e.m[0];
+        a.tw = tw_[0]; a.tw_n = tw_n_[0]; a.twist = 2;
+        LMC_TRY(launch_pass(a, true, true, st));
+    }
     return 0;
 }
 

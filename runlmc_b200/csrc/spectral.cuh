@@ -43,12 +43,25 @@ class SpectralEngine {
 
     size_t work_elems(int nslab) const { return (size_t)nslab * emb_.bins; }
 
+    // ---- fused path: G <- (sum_q B_q (x) T_q) G in place on the grid slabs ----
+    // 2-D: transposing row pass -> [column FFT + mix + inverse column FFT in one kernel] -> row pass;
+    // 1-D: one kernel (lines fit a CTA) or the four-step outer passes around the fused inner kernel.
+    bool fused_supported(int D, int Q) const;
+    // elements of scratch S needed per RHS pair on the fused path
+    size_t fused_elems_per_pair(int D) const;
+    // line-major spectra for the fused kernel: specL[q][line][pos]  (2-D: transposed copy of spec)
+    int spectrum_lines(const double* spec, double* specL, int Q, cudaStream_t st);
+    int apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL,
+                    const double* B_host /*[Q][D][D] host*/, cudaStream_t st);
+
   private:
     Embedding emb_;
     cplx* tw_[3] = {nullptr, nullptr, nullptr};  // per-axis twiddle tables exp(-2 pi i k / mt_p)
     int tw_n_[3] = {0, 0, 0};
     FftPlan plan_[3];
     FftPlan plan1_, plan2_;                       // four-step sub-plans
+    cplx* stage_tw_rows_ = nullptr;               // same for the transposing row pass (2-D)
+    cplx* stage_tw_ = nullptr;                    // per-stage twiddles of the fused kernel's line length
 };
 
 // real grid vectors X[k][D*m] <-> complex pair slabs Z[ceil(k/2)][D][gpitch]

@@ -8,7 +8,7 @@ def probe(name, P, cpl, iters=5, **kw):
     t1 = time.time()
     op = FusedLMC(prob.Xs, prob.grids); op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
     t2 = time.time()
-    print(f'{name}: n={prob.n} gen {t1-t0:.1f}s create {t2-t1:.2f}s')
+    print(f'{name}: n={prob.n} gen {t1-t0:.1f}s create {t2-t1:.2f}s max_tile_pts', nat.lib.lmc_op_max_tile_points(op._h))
     V = torch.randn(P, prob.n, dtype=torch.float64, device='cuda')
     out = torch.empty_like(V)
     for _ in range(2): op.mvm_device(V, out)
@@ -34,3 +34,17 @@ torch.cuda.synchronize(); t = time.time()
 X, it, res, st = op.minres_device(R, tol=1e-4, maxiter=20, check_every=100)
 torch.cuda.synchronize(); dt = time.time() - t
 print('E minres 17 rhs x 20 iters: %.3f s -> %.0f iter*rhs/s' % (dt, 17*20/dt), it[:4], res[:4])
+# same E problem with inputs pre-sorted into the operator's order (perm = identity)
+perm = op.perm()
+off = np.concatenate([[0], np.cumsum(prob.lens)])
+Xall = np.vstack(prob.Xs)[perm]
+prob.Xs = [Xall[off[d]:off[d+1]] for d in range(prob.D)]
+op2 = FusedLMC(prob.Xs, prob.grids); op2.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+assert np.all(op2.perm() == np.arange(prob.n))
+V = torch.randn(129, prob.n, dtype=torch.float64, device='cuda'); out = torch.empty_like(V)
+for _ in range(2): op2.mvm_device(V, out)
+nat.profile_begin()
+for _ in range(5): op2.mvm_device(V, out)
+prof = nat.profile_end()
+print('E with identity perm:')
+for k, (m, c) in prof.items(): print(f'    {k:18s} {m/5:8.3f} ms/step')

@@ -133,7 +133,7 @@ def test_minres_against_reference_golden(name):
         ref_res = np.linalg.norm(b - ref.matvec(w))
         # reported residual is the true residual, and as good as the reference's
         assert abs(r - np.linalg.norm(b - ref.matvec(x))) <= 1e-9 + 1e-6 * r
-        assert r <= max(1e-4, 3 * ref_res)
+        assert r <= max(3e-4, 5 * ref_res)
 
 
 @pytest.mark.parametrize('name', ['A', '2d_small', 'd_small'])
