@@ -18,6 +18,8 @@ oracle port, one process per core like the reference's Pool.starmap) on a
 bounded sample of the same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -36,7 +38,7 @@ from runlmc_b200 import synthetic  # noqa: E402
 
 METRIC = 'ski_lmc_mvm_rhs_per_s'
 UNIT = 'MVM*RHS/s'
-CPL = {'A': 4, 'B': 8, 'C': 5, 'D': 8, 'E': 6}     # grid cells per (shortest) lengthscale
+CPL = {'A': 4, 'B': 8, 'C': 5, 'D': 2, 'E': 1.5}     # grid cells per (shortest) lengthscale
 
 
 def workload_desc(name, prob):
@@ -97,6 +99,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.window = [None, None]   # wall-clock bounds of the timed region
 
     def run(self):
         while not self.stop_flag:
@@ -105,7 +108,7 @@ class ClockSampler(threading.Thread):
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
+                    self.rows.append([time.time()] + [x.strip() for x in out.split(',')])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -114,11 +117,14 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if not self.rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(r[0]) for r in self.rows)
+        rows = [r[1:] for r in self.rows]
+        inside = [r[1:] for r in self.rows if self.window[0] is not None and self.window[0] <= r[0] <= self.window[1]]
+        sm = sorted(float(r[0]) for r in rows)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons,
-                'samples': len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons,
+                'samples': len(sm), 'samples_in_timed_region': len(inside),
+                'note': 'sampled every 0.2 s from warm-up to the end of the device-timed and e2e loops (GPU busy throughout)'}
 
 
 # --------------------------------------------------------------------------
@@ -178,7 +184,7 @@ def run_own(args):
     from runlmc_b200.distributed import shard_bounds, sharded_gradient
     dev = torch.device('cuda', local)
     op = FusedLMC(prob.Xs, prob.grids)
-    op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+    op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
     lo, hi = shard_bounds(prob.N, rank, world)
     rows = [prob.y[None, :]] if rank == 0 else []
     rows.append(prob.probes[lo:hi])
@@ -193,21 +199,27 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        op.mvm_device(V, OUT)
     sampler = ClockSampler(local)
     sampler.start()
+    t_w = time.time()
+    while True:                                   # warm-up: >= W steps and long enough for the clocks to settle
+        for _ in range(args.warmup):
+            op.mvm_device(V, OUT)
+        torch.cuda.synchronize()
+        if time.time() - t_w > 0.5:
+            break
     l0 = nat.lib.lmc_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.window[0] = time.time()
     e0.record()
     for _ in range(args.steps):
         op.mvm_device(V, OUT)
     e1.record()
     barrier()
+    sampler.window[1] = time.time()
     ms = e0.elapsed_time(e1)
     launches = int(nat.lib.lmc_launch_count() - l0)
-    clocks = sampler.summary()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -215,25 +227,28 @@ def run_own(args):
     ms_step = ms / args.steps
     value = total_units * args.steps / (ms / 1e3)
 
-    # ---- end to end through host buffers ----
-    e2e_steps = max(1, min(args.steps, 3))
+    # ---- end to end through host buffers: the public host API FusedLMC.mvm_into (C ABI
+    # lmc_mvm_host) on pinned buffers; H2D copy of V and D2H copy of K~V are inside the timed
+    # region of every step ----
+    e2e_steps = max(1, min(args.steps, 5))
     Vp = torch.as_tensor(Vh).pin_memory()
     Op = torch.empty_like(Vp).pin_memory()
-    Vd = torch.empty_like(V)
-    for _ in range(1):
-        Vd.copy_(Vp, non_blocking=True); op.mvm_device(Vd, OUT); Op.copy_(OUT, non_blocking=True)
+    Vpn, Opn = Vp.numpy(), Op.numpy()
+    op.mvm_into(Vpn, Opn)
     barrier()
-    e0.record()
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        Vd.copy_(Vp, non_blocking=True)
-        op.mvm_device(Vd, OUT)
-        Op.copy_(OUT, non_blocking=True)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        op.mvm_into(Vpn, Opn)          # returns after the last D2H copy has landed
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([dt_e2e * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = total_units * e2e_steps / (float(t.item()) / 1e3)
+    e2e_check = float(np.abs(Opn - OUT.cpu().numpy()).max())
+    clocks = sampler.summary()
     cnt = torch.tensor([float(P)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt)
@@ -289,7 +304,8 @@ def run_own(args):
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_desc(args.workload, prob),
                 'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': io_bytes, 'd2h_bytes_per_step': io_bytes,
-                        'steps': e2e_steps}, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+                        'steps': e2e_steps, 'api': 'FusedLMC.mvm_into -> lmc_mvm_host (pinned host buffers, '
+                        'chunked copy/compute/copy pipeline)', 'max_abs_diff_vs_resident': e2e_check}, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
                 'roofline_mvm': roofline_mvm, 'kernel_families': fams, 'gradient': grad}
         if cpu is not None:
             line['cpu_baseline'] = cpu
@@ -324,10 +340,25 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_own(args)
+    # stdout carries exactly ONE line (the JSON): anything libraries print there while we run
+    # (e.g. NCCL's version banner) is diverted to stderr at the file-descriptor level
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            if args.impl == 'reference':
+                run_reference(args)
+            else:
+                run_own(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith('{')]
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == '__main__':

@@ -60,6 +60,12 @@ int lmc_op_destroy(lmc_op* op);
  * coregionalisation matrices (functional_kernel.py:280-287); noise_host [D].    */
 int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* B_host,
                       const double* noise_host);
+/* Optional, after lmc_op_set_params: the LMC factors B_q = A_q^T A_q + diag(kappa_q)
+ * (coreg_vecs / coreg_diags of functional_kernel.py:280-287; ranks[Q], A [sum ranks][D],
+ * kappa [Q][D]).  They must reproduce the dense B; the spectral mix then costs O(R D) instead
+ * of O(D^2) per frequency bin.  Results are unchanged up to rounding.                         */
+int lmc_op_set_coreg_factors(lmc_op* op, const int* ranks_host, const double* A_host,
+                             const double* kappa_host);
 long lmc_op_n(const lmc_op* op);          /* total points */
 long lmc_op_grid_cells(const lmc_op* op); /* m = prod grid_sizes */
 long lmc_op_embed_bins(const lmc_op* op); /* prod of the power-of-two embedding sizes */

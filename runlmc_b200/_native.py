@@ -43,6 +43,7 @@ SIGNATURES = {
     'lmc_op_create': (_i, [ctypes.POINTER(_p), _i, _i, _p, _p, _p, _p, _p]),
     'lmc_op_destroy': (_i, [_p]),
     'lmc_op_set_params': (_i, [_p, _i, _p, _p, _p]),
+    'lmc_op_set_coreg_factors': (_i, [_p, _p, _p, _p]),
     'lmc_op_n': (_l, [_p]),
     'lmc_op_grid_cells': (_l, [_p]),
     'lmc_op_embed_bins': (_l, [_p]),

@@ -2,6 +2,8 @@
 #include "../../include/lmc_b200.h"
 #include "op.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -74,7 +76,39 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
     if (rc != 0) return rc;
     LMC_CHECK(e);
     op->B_host.assign(B_host, B_host + (size_t)Q * D * D);
+    op->ranks.clear();
+    op->A_host.clear();
+    op->kappa_host.clear();
     op->Q = Q;
+    return 0;
+}
+
+int lmc_op_set_coreg_factors(lmc_op* op, const int* ranks_host, const double* A_host,
+                             const double* kappa_host) {
+    LMC_REQUIRE(op && ranks_host && A_host && kappa_host, "null argument");
+    LMC_REQUIRE(op->Q > 0, "call lmc_op_set_params first");
+    const int D = op->D, Q = op->Q;
+    int total = 0;
+    for (int q = 0; q < Q; ++q) {
+        LMC_REQUIRE(ranks_host[q] >= 0, "negative rank");
+        total += ranks_host[q];
+    }
+    // the factors must reproduce the dense matrices uploaded by lmc_op_set_params
+    int r0 = 0;
+    for (int q = 0; q < Q; ++q) {
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double v = (i == j) ? kappa_host[(size_t)q * D + i] : 0.0;
+                for (int r = r0; r < r0 + ranks_host[q]; ++r) v += A_host[(size_t)r * D + i] * A_host[(size_t)r * D + j];
+                const double b = op->B_host[((size_t)q * D + i) * D + j];
+                LMC_REQUIRE(std::fabs(v - b) <= 1e-12 * (1.0 + std::fabs(b)),
+                            "coregionalisation factors do not match B_q = A_q^T A_q + diag(kappa_q)");
+            }
+        r0 += ranks_host[q];
+    }
+    op->ranks.assign(ranks_host, ranks_host + Q);
+    op->A_host.assign(A_host, A_host + (size_t)total * D);
+    op->kappa_host.assign(kappa_host, kappa_host + (size_t)Q * D);
     return 0;
 }
 
@@ -98,17 +132,64 @@ int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, vo
     return op_mvm(op, cv, (cudaStream_t)stream);
 }
 
+// Host buffers in, host buffers out.  The block is cut into chunks of columns that flow through a
+// 3-stage pipeline (H2D copy | product | D2H copy) on three streams with double-buffered device
+// staging, so PCIe traffic in both directions overlaps the kernels.  With pinned host memory the
+// copies are truly asynchronous; pageable memory works too (the driver stages it).
 int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_host) {
     LMC_REQUIRE(op && V_host && OUT_host, "null argument");
     LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
     if (P == 0) return 0;
-    HostBlock in, out;
-    const size_t bytes = sizeof(double) * (size_t)P * ld;
-    LMC_CHECK(cudaMalloc(&in.p, bytes));
-    LMC_CHECK(cudaMalloc(&out.p, bytes));
-    LMC_CHECK(cudaMemcpy(in.p, V_host, bytes, cudaMemcpyHostToDevice));
-    LMC_TRY(lmc_mvm(op, in.p, ld, P, out.p, nullptr));
-    LMC_CHECK(cudaMemcpy(OUT_host, out.p, bytes, cudaMemcpyDeviceToHost));
+    const long n = op->ps.n;
+    // chunk width: even, ~64 MB per buffer, at least 2 and at most 32 columns
+    int chunk = (int)std::max<long>(2, std::min<long>(32, (64L << 20) / (8 * n)));
+    chunk &= ~1;
+    chunk = std::min(chunk, (P + 1) & ~1);
+    const size_t need = (size_t)chunk * n;
+    if (!op->hs[0]) {
+        for (int i = 0; i < 3; ++i) LMC_CHECK(cudaStreamCreateWithFlags(&op->hs[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_in[i], cudaEventDisableTiming));
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_cmp[i], cudaEventDisableTiming));
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (need > op->stage_cap) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(op->stage_in[i]); cudaFree(op->stage_out[i]);
+            op->stage_in[i] = op->stage_out[i] = nullptr;
+        }
+        op->stage_cap = 0;
+        for (int i = 0; i < 2; ++i) {
+            LMC_CHECK(cudaMalloc(&op->stage_in[i], sizeof(double) * need));
+            LMC_CHECK(cudaMalloc(&op->stage_out[i], sizeof(double) * need));
+        }
+        op->stage_cap = need;
+    }
+    cudaStream_t s_in = op->hs[0], s_cmp = op->hs[1], s_out = op->hs[2];
+    int k = 0;
+    for (int c0 = 0; c0 < P; c0 += chunk, ++k) {
+        const int b = k & 1;
+        const int cnt = std::min(chunk, P - c0);
+        if (k >= 2) LMC_CHECK(cudaStreamWaitEvent(s_in, op->ev_cmp[b], 0));    // staging buffer consumed
+        LMC_CHECK(cudaMemcpy2DAsync(op->stage_in[b], sizeof(double) * n, V_host + (size_t)c0 * ld,
+                                    sizeof(double) * ld, sizeof(double) * n, cnt, cudaMemcpyHostToDevice, s_in));
+        LMC_CHECK(cudaEventRecord(op->ev_in[b], s_in));
+        LMC_CHECK(cudaStreamWaitEvent(s_cmp, op->ev_in[b], 0));
+        if (k >= 2) LMC_CHECK(cudaStreamWaitEvent(s_cmp, op->ev_out[b], 0));  // previous result copied out
+        ColumnView cv;
+        cv.in = op->stage_in[b]; cv.out = op->stage_out[b]; cv.ld = n; cv.ncols = cnt;
+        LMC_TRY(op_mvm(op, cv, s_cmp));
+        LMC_CHECK(cudaEventRecord(op->ev_cmp[b], s_cmp));
+        LMC_CHECK(cudaStreamWaitEvent(s_out, op->ev_cmp[b], 0));
+        LMC_CHECK(cudaMemcpy2DAsync(OUT_host + (size_t)c0 * ld, sizeof(double) * ld, op->stage_out[b],
+                                    sizeof(double) * n, sizeof(double) * n, cnt, cudaMemcpyDeviceToHost, s_out));
+        LMC_CHECK(cudaEventRecord(op->ev_out[b], s_out));
+    }
+    LMC_CHECK(cudaStreamSynchronize(s_out));
+    LMC_CHECK(cudaStreamSynchronize(s_cmp));
+    LMC_CHECK(cudaStreamSynchronize(s_in));
     return 0;
 }
 

@@ -366,6 +366,26 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// Solver workspace kept between calls (grow-only): cudaMalloc/cudaFree of ~8 n P doubles per solve
+// would otherwise cost as much as tens of iterations.
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~Workspace() { if (p) cudaFree(p); }
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        LMC_CHECK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return 0;
+    }
+};
+static Workspace g_ws;
+struct WsSlice {
+    char* p;
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
 static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, double* X, double tol,
                        int maxiter, int check_every, int* iters, double* resid, int* istop,
                        cudaStream_t st) {
@@ -376,8 +396,11 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
     const int nblk = ceil_div(n, kVecChunk);
     const double rtol = std::fmin(1e-10, tol);
     const size_t vec = sizeof(double) * (size_t)P * n;
-    DevBuf bufs[8], parts[3], stb, invb, act, nact;
-    for (auto& b : bufs) LMC_TRY(b.alloc(vec));
+    DevBuf parts[3], stb, invb, act, nact;
+    const size_t vec_al = (vec + 255) & ~(size_t)255;
+    LMC_TRY(g_ws.reserve(vec_al * 8));
+    WsSlice bufs[8];
+    for (int i = 0; i < 8; ++i) bufs[i].p = static_cast<char*>(g_ws.p) + vec_al * i;
     for (auto& b : parts) LMC_TRY(b.alloc(sizeof(double) * (size_t)P * nblk));
     LMC_TRY(stb.alloc(sizeof(ColState) * P));
     LMC_TRY(invb.alloc(sizeof(double) * P));

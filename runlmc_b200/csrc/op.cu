@@ -75,7 +75,7 @@ int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st) {
         const int qc = std::min(step, cnt - q0);
         cplx* g = G + (size_t)q0 * slab;
         if (op->fused)
-            LMC_TRY(op->eng.apply_fused(g, op->S, qc, op->D, op->Q, op->specL, op->B_host.data(), st));
+            LMC_TRY(op->eng.apply_fused(g, op->S, qc, op->D, op->Q, op->specL, op->mix_spec(), st));
         else
             LMC_TRY(op_grid_apply(op, g, qc, op->Q, op->spec, op->B, st));
     }
@@ -106,6 +106,15 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
 
 lmc_op::~lmc_op() {
     lmc::free_points(&ps);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(stage_in[i]);
+        cudaFree(stage_out[i]);
+        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+        if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
+        if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+    }
+    for (int i = 0; i < 3; ++i)
+        if (hs[i]) cudaStreamDestroy(hs[i]);
     cudaFree(spec);
     cudaFree(specL);
     cudaFree(B);

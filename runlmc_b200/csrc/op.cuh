@@ -13,6 +13,14 @@ struct lmc_op {
     double* spec = nullptr;   // [Q][bins] real circulant spectra / bins (digit-reversed layout)
     double* specL = nullptr;  // [Q][line][pos] line-major copy for the fused spectral kernel
     std::vector<double> B_host;
+    std::vector<int> ranks;          // optional factors B_q = A_q^T A_q + diag(kappa_q)
+    std::vector<double> A_host, kappa_host;
+    lmc::MixSpec mix_spec() const {
+        lmc::MixSpec m;
+        m.B = B_host.data();
+        if (!ranks.empty()) { m.ranks = ranks.data(); m.A = A_host.data(); m.kappa = kappa_host.data(); }
+        return m;
+    }
     bool fused = false;       // fused spectral path usable for this geometry / D / Q
     int fused_tile_pairs = 0;
     double* B = nullptr;      // [Q][D][D]
@@ -23,6 +31,12 @@ struct lmc_op {
     cplx* S = nullptr;        // [tile_pairs][D][bins]     spectra of one L2-sized sub-tile of pairs
     int g_pairs = 0;
     int tile_pairs = 0;
+    // host-buffer entry points: double-buffered device staging + 3 streams (copy in / compute / copy out)
+    double* stage_in[2] = {nullptr, nullptr};
+    double* stage_out[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;   // doubles per staging buffer
+    cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     ~lmc_op();
 };
 

@@ -425,9 +425,21 @@ __global__ void __launch_bounds__(256) fft_rows_T_kernel(const RowsTArgs a) {
             st[(long)e * a.xpitch + x0 + l] = tile[l * pitch + pad_idx(e)];
         }
     } else {
-        for (int idx = threadIdx.x; idx < L * nr; idx += blockDim.x) {
-            const int e = idx >> a.lnr, l = idx & (nr - 1);
-            tile[l * pitch + pad_idx(e)] = st[(long)e * a.xpitch + x0 + l];
+        // transposed load, 8 independent 16-byte loads in flight per thread
+        for (int idx0 = threadIdx.x; idx0 < L * nr; idx0 += 8 * blockDim.x) {
+            cplx v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = idx0 + u * blockDim.x;
+                const int e = idx >> a.lnr, l = idx & (nr - 1);
+                if (idx < L * nr) v[u] = st[(long)e * a.xpitch + x0 + l];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = idx0 + u * blockDim.x;
+                const int e = idx >> a.lnr, l = idx & (nr - 1);
+                if (idx < L * nr) tile[l * pitch + pad_idx(e)] = v[u];
+            }
         }
         __syncthreads();
         cplx* g = a.G_out + slab * a.g_slab;
@@ -442,9 +454,79 @@ __global__ void __launch_bounds__(256) fft_rows_T_kernel(const RowsTArgs a) {
 // Forward transform of the D lines of one RHS pair, per-bin coregionalisation mix, inverse
 // transform -- all in shared memory, in place on global memory.  The mixing matrices travel as
 // kernel parameters so they are constant-bank operands of the DFMAs.
+// Mixing operators, passed as kernel parameters (constant-bank operands).
+// Dense:    y = (sum_q f_q B_q) x                      (Q + 2) D^2 DFMA per bin and RHS pair
+// Low rank: B_q = A_q^T A_q + diag(kappa_q) (the LMC parameterisation, reference
+//           functional_kernel.py:280-287):  y = sum_q f_q A_q^T (A_q x) + (sum_q f_q kappa_q) .* x
+//           sum_q R_q (4D + 2) + (Q + 2) D DFMA
 template <int D>
 struct MixB {
     double b[8][D][D];
+    __device__ __forceinline__ void apply(const double* f, int Q, const cplx* x, cplx* y) const {
+#pragma unroll
+        for (int dp = 0; dp < D; ++dp) {
+            double m[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) m[d] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < Q) {   // warp-uniform
+#pragma unroll
+                    for (int d = 0; d < D; ++d) m[d] = fma(f[q], b[q][dp][d], m[d]);
+                }
+            }
+            double yr = 0.0, yi = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                yr = fma(m[d], x[d].x, yr);
+                yi = fma(m[d], x[d].y, yi);
+            }
+            y[dp] = make_double2(yr, yi);
+        }
+    }
+};
+
+static const int kMaxRankPerKernel = 2;   // low-rank path: every B_q has rank <= 2 (+ diagonal)
+template <int D>
+struct MixLR {
+    double a[8][kMaxRankPerKernel][D];
+    double kappa[8][D];
+    int rank[8];
+    __device__ __forceinline__ void apply(const double* f, int Q, const cplx* x, cplx* y) const {
+        double ks[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { ks[d] = 0.0; y[d] = make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q < Q) {   // warp-uniform
+#pragma unroll
+                for (int r = 0; r < kMaxRankPerKernel; ++r) {
+                    if (r < rank[q]) {   // warp-uniform
+                        double tr = 0.0, ti = 0.0;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            tr = fma(a[q][r][d], x[d].x, tr);
+                            ti = fma(a[q][r][d], x[d].y, ti);
+                        }
+                        tr *= f[q];
+                        ti *= f[q];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            y[d].x = fma(a[q][r][d], tr, y[d].x);
+                            y[d].y = fma(a[q][r][d], ti, y[d].y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) ks[d] = fma(f[q], kappa[q][d], ks[d]);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            y[d].x = fma(ks[d], x[d].x, y[d].x);
+            y[d].y = fma(ks[d], x[d].y, y[d].y);
+        }
+    }
 };
 
 struct FusedArgs {
@@ -460,8 +542,8 @@ struct FusedArgs {
     int pitch, half;
 };
 
-template <int D>
-__global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, const MixB<D> mb) {
+template <int D, class MIX>
+__global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, const MIX mb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tws = reinterpret_cast<cplx*>(smem_raw);            // per-stage twiddle tables
     cplx* tile = tws + a.tw_total;                            // [lpc*D][pitch]
@@ -493,26 +575,10 @@ __global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, 
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             f[q] = (q < a.Q) ? __ldg(&a.specL[((long)q * a.n_lines + line0 + ll) * L + p]) : 0.0;
+        cplx y[D];
+        mb.apply(f, a.Q, x, y);
 #pragma unroll
-        for (int dp = 0; dp < D; ++dp) {
-            double m[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) m[d] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (q < a.Q) {   // warp-uniform
-#pragma unroll
-                    for (int d = 0; d < D; ++d) m[d] = fma(f[q], mb.b[q][dp][d], m[d]);
-                }
-            }
-            double yr = 0.0, yi = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                yr = fma(m[d], x[d].x, yr);
-                yi = fma(m[d], x[d].y, yi);
-            }
-            col[dp * pitch] = make_double2(yr, yi);
-        }
+        for (int d = 0; d < D; ++d) col[d * pitch] = y[d];
     }
     __syncthreads();
     for (int li = warp; li < nl; li += nwarps) {
@@ -553,12 +619,31 @@ __global__ void stage_twiddle_kernel(cplx* tab, int L, FftPlan pl, StageTw lay) 
 static const size_t kFusedSmemMax = 200 * 1024;
 
 template <int D>
-static int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const double* B_host, int npairs,
+static int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, int npairs,
                               cudaStream_t st) {
     static MixB<D> mb;   // zero-initialised; only the first Q blocks are read
-    for (int q = 0; q < a.Q; ++q)
-        for (int i = 0; i < D; ++i)
-            for (int j = 0; j < D; ++j) mb.b[q][i][j] = B_host[((size_t)q * D + i) * D + j];
+    static MixLR<D> ml;
+    int total_rank = 0, max_rank = 0;
+    if (mix.ranks)
+        for (int q = 0; q < a.Q; ++q) {
+            total_rank += mix.ranks[q];
+            max_rank = std::max(max_rank, mix.ranks[q]);
+        }
+    const bool lowrank = mix.ranks && max_rank <= kMaxRankPerKernel &&
+                         total_rank * (4 * D + 2) + (a.Q + 2) * D < (a.Q + 2) * D * D;
+    if (lowrank) {
+        int r = 0;
+        for (int q = 0; q < a.Q; ++q) {
+            ml.rank[q] = mix.ranks[q];
+            for (int k = 0; k < mix.ranks[q]; ++k, ++r)
+                for (int d = 0; d < D; ++d) ml.a[q][k][d] = mix.A[(size_t)r * D + d];
+            for (int d = 0; d < D; ++d) ml.kappa[q][d] = mix.kappa[(size_t)q * D + d];
+        }
+    } else {
+        for (int q = 0; q < a.Q; ++q)
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) mb.b[q][i][j] = mix.B[((size_t)q * D + i) * D + j];
+    }
     a.plan = make_plan(a.L);
     a.lay = stage_tw_layout(a.L, a.plan);
     a.tw_total = a.lay.total;
@@ -573,14 +658,17 @@ static int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const double* B
     LMC_REQUIRE(smem <= kFusedSmemMax, "fused spectral tile does not fit shared memory");
     static bool attr = false;
     if (!attr) {
-        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kFusedSmemMax));
+        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MixB<D>>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
+        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MixLR<D>>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
         attr = true;
     }
     const int threads = 32 * std::max(2, std::min(10, lpc * D));   // one warp per line, up to 10 warps
     dim3 grid((unsigned)ceil_div(a.n_lines, lpc), (unsigned)npairs);
     ProfScope prof(PROF_MIX, st);
-    fused_lines_kernel<D><<<grid, threads, smem, st>>>(a, mb);
+    if (lowrank) fused_lines_kernel<D, MixLR<D>><<<grid, threads, smem, st>>>(a, ml);
+    else fused_lines_kernel<D, MixB<D>><<<grid, threads, smem, st>>>(a, mb);
     count_launch();
     LMC_CHECK(cudaGetLastError());
     return 0;
@@ -832,7 +920,7 @@ int SpectralEngine::spectrum_lines(const double* spec, double* specL, int Q, cud
 }
 
 int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL,
-                                const double* B_host, cudaStream_t st) {
+                                const MixSpec& mix, cudaStream_t st) {
     if (npairs == 0) return 0;
     const Embedding& e = emb_;
     FusedArgs f = {};
@@ -891,7 +979,7 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         f.n_lines = e.mt[1]; f.L = e.mt[0]; f.valid = e.m[0];
         int rc = 1;
         switch (D) {
-#define LMC_FUSED_CASE(DD) case DD: rc = launch_fused_lines<DD>(f, stw, B_host, npairs, st); break;
+#define LMC_FUSED_CASE(DD) case DD: rc = launch_fused_lines<DD>(f, stw, mix, npairs, st); break;
             LMC_FUSED_CASE(1) LMC_FUSED_CASE(2) LMC_FUSED_CASE(3) LMC_FUSED_CASE(4) LMC_FUSED_CASE(5)
             LMC_FUSED_CASE(6) LMC_FUSED_CASE(7) LMC_FUSED_CASE(8) LMC_FUSED_CASE(9) LMC_FUSED_CASE(10)
             LMC_FUSED_CASE(11) LMC_FUSED_CASE(12) LMC_FUSED_CASE(13) LMC_FUSED_CASE(14) LMC_FUSED_CASE(15)

@@ -21,6 +21,15 @@ struct Embedding {
 
 int embedding_init(Embedding* e, int ndim, const int* sizes);
 
+// Host description of the coregionalisation mix: dense B [Q][D][D], optionally with the factors of
+// B_q = A_q^T A_q + diag(kappa_q)  (ranks[Q], A [sum ranks][D], kappa [Q][D]).
+struct MixSpec {
+    const double* B = nullptr;
+    const int* ranks = nullptr;
+    const double* A = nullptr;
+    const double* kappa = nullptr;
+};
+
 class SpectralEngine {
   public:
     ~SpectralEngine();
@@ -51,8 +60,8 @@ class SpectralEngine {
     size_t fused_elems_per_pair(int D) const;
     // line-major spectra for the fused kernel: specL[q][line][pos]  (2-D: transposed copy of spec)
     int spectrum_lines(const double* spec, double* specL, int Q, cudaStream_t st);
-    int apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL,
-                    const double* B_host /*[Q][D][D] host*/, cudaStream_t st);
+    int apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL, const MixSpec& mix,
+                    cudaStream_t st);
 
   private:
     Embedding emb_;

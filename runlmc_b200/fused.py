@@ -62,9 +62,12 @@ class FusedLMC:
                 pass
 
     # ---- parameters ------------------------------------------------------
-    def set_params(self, tops, Bs, noise):
+    def set_params(self, tops, Bs, noise, coreg_vecs=None, coreg_diags=None):
         """tops: Q arrays of kernel values on the grid (any shape with m
-        entries); Bs: Q (D, D) coregionalisation matrices; noise: (D,)."""
+        entries); Bs: Q (D, D) coregionalisation matrices; noise: (D,).
+        Optionally the LMC factors with Bs[q] = coreg_vecs[q].T @ coreg_vecs[q]
+        + diag(coreg_diags[q]) (functional_kernel.py:280-287), which make the
+        spectral mix cheaper."""
         tops = nat.as_f64(np.array([np.asarray(t, dtype=np.float64).ravel()
                                     for t in tops]))
         Bs = nat.as_f64(np.array(Bs))
@@ -79,6 +82,15 @@ class FusedLMC:
         nat.check(nat.lib.lmc_op_set_params(
             self._h, Q, nat.host_ptr(tops), nat.host_ptr(Bs), nat.host_ptr(noise)))
         self.Q = Q
+        if coreg_vecs is not None and coreg_diags is not None:
+            vecs = [np.atleast_2d(np.asarray(a, dtype=np.float64)) for a in coreg_vecs]
+            ranks = nat.as_i32([len(a) for a in vecs])
+            A = nat.as_f64(np.vstack(vecs))
+            kappa = nat.as_f64(np.array(coreg_diags))
+            if len(vecs) != Q or A.shape[1] != self.D or kappa.shape != (Q, self.D):
+                raise ValueError('coregionalisation factors have the wrong shape')
+            nat.check(nat.lib.lmc_op_set_coreg_factors(
+                self._h, nat.host_ptr(ranks), nat.host_ptr(A), nat.host_ptr(kappa)))
 
     def perm(self):
         p = np.empty(self.n, dtype=np.int32)
@@ -102,6 +114,14 @@ class FusedLMC:
         nat.check(nat.lib.lmc_mvm_host(self._h, nat.host_ptr(V), self.n,
                                         V.shape[0], nat.host_ptr(out)))
         return out[0] if single else out
+
+    def mvm_into(self, V, out):
+        """Host-buffer product without allocations: V, out are C-contiguous float64
+        [P, n] arrays (pin them, e.g. torch's pin_memory().numpy(), for full PCIe
+        overlap).  Copy-in, product and copy-out are pipelined over column chunks."""
+        assert V.flags['C_CONTIGUOUS'] and out.flags['C_CONTIGUOUS'] and V.shape == out.shape
+        nat.check(nat.lib.lmc_mvm_host(self._h, nat.host_ptr(V), self.n, V.shape[0], nat.host_ptr(out)))
+        return out
 
     def matvec(self, x):
         return self.mvm(np.asarray(x, dtype=np.float64).reshape(-1))

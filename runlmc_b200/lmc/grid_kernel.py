@@ -99,7 +99,10 @@ def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
         cache = FusedLMC(Xs, grids)          # X-dependent sort happens once per model
         W._lmc_fused = cache
     grid_k = fk.eval_kernels_fixed_dim(grid_dists[active_dim], active_dim)
-    cache.set_params(list(grid_k), fk.coreg_mats(active_dim), fk.noise)
+    idxs = fk.active_dims[active_dim]
+    cache.set_params(list(grid_k), fk.coreg_mats(active_dim), fk.noise,
+                     coreg_vecs=[fk.coreg_vecs[i] for i in idxs],
+                     coreg_diags=[fk.coreg_diags[i] for i in idxs])
     return cache
 
 

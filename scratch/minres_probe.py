@@ -4,7 +4,7 @@ from runlmc_b200 import synthetic
 from runlmc_b200.fused import FusedLMC
 name = sys.argv[1]; cpl = float(sys.argv[2]); nrhs = int(sys.argv[3])
 prob = synthetic.make_problem(name, seed=1234, cells_per_lengthscale=cpl)
-op = FusedLMC(prob.Xs, prob.grids); op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+op = FusedLMC(prob.Xs, prob.grids); op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
 R = torch.tensor(np.vstack([prob.y[None], prob.probes[:nrhs-1]]), device='cuda')
 torch.cuda.synchronize(); t = time.time()
 X, it, res, st = op.minres_device(R, tol=1e-4, maxiter=3000)

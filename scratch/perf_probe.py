@@ -6,7 +6,7 @@ def probe(name, P, cpl, iters=5, **kw):
     t0 = time.time()
     prob = synthetic.make_problem(name, seed=1234, cells_per_lengthscale=cpl, **kw)
     t1 = time.time()
-    op = FusedLMC(prob.Xs, prob.grids); op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+    op = FusedLMC(prob.Xs, prob.grids); op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
     t2 = time.time()
     print(f'{name}: n={prob.n} gen {t1-t0:.1f}s create {t2-t1:.2f}s max_tile_pts', nat.lib.lmc_op_max_tile_points(op._h))
     V = torch.randn(P, prob.n, dtype=torch.float64, device='cuda')
@@ -39,7 +39,7 @@ perm = op.perm()
 off = np.concatenate([[0], np.cumsum(prob.lens)])
 Xall = np.vstack(prob.Xs)[perm]
 prob.Xs = [Xall[off[d]:off[d+1]] for d in range(prob.D)]
-op2 = FusedLMC(prob.Xs, prob.grids); op2.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+op2 = FusedLMC(prob.Xs, prob.grids); op2.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
 assert np.all(op2.perm() == np.arange(prob.n))
 V = torch.randn(129, prob.n, dtype=torch.float64, device='cuda'); out = torch.empty_like(V)
 for _ in range(2): op2.mvm_device(V, out)

@@ -13,10 +13,15 @@ MVM_TOL = 1e-10      # north_star: MVMs within 1e-10 relative
 GRAD_TOL = 1e-8      # north_star: gradient within 1e-8 relative (identical probes)
 
 
-def fused_from_problem(prob):
+def fused_from_problem(prob, factors=True):
+    """factors=True also hands over the LMC factors B_q = A_q^T A_q + diag(kappa_q),
+    which selects the low-rank spectral mix where it is cheaper."""
     from runlmc_b200.fused import FusedLMC
     op = FusedLMC(prob.Xs, prob.grids)
-    op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
+    if factors:
+        op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+    else:
+        op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
     return op
 
 
@@ -86,6 +91,21 @@ def test_mvm_against_reference_golden(name):
     got = op.mvm(g['V'])
     for a, b in zip(got, g['KV']):
         assert rel_err(a, b) < MVM_TOL
+
+
+@pytest.mark.parametrize('name', ['2d_small', 'd_small', 'C', 'four_step'])
+def test_lowrank_mix_equals_dense_mix(name):
+    prob = PROBLEMS[name]()
+    rng = np.random.default_rng(3)
+    V = rng.standard_normal((3, prob.n))
+    a = fused_from_problem(prob, factors=True).mvm(V)
+    b = fused_from_problem(prob, factors=False).mvm(V)
+    assert rel_err(a, b) < 1e-13
+    from runlmc_b200.fused import FusedLMC
+    op = FusedLMC(prob.Xs, prob.grids)
+    with pytest.raises(ValueError):        # factors must reproduce B
+        op.set_params(prob.tops, prob.coreg_mats(), prob.noise,
+                      [2 * a_ for a_ in prob.coreg_vecs], prob.coreg_diags)
 
 
 def test_linearity_and_symmetry_large():
