@@ -93,38 +93,76 @@ def cpu_reference_rate(prob, steps, warmup, cores=None, budget_s=25.0):
 # clocks
 # --------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled from a host thread every few ms through
+    NVML (in-process; `nvidia-smi` subprocess as a fallback) so that even a ~100 ms timed region
+    holds several samples.  `window` = wall-clock bounds of the device-timed region."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
-        self.window = [None, None]   # wall-clock bounds of the timed region
+        self.index, self.period, self.rows, self.stop_flag = index, period, [], False
+        self.window = [None, None]
+        self.nvml = self.h = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(',')]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        flags = [bool(r & n.nvmlClocksEventReasonHwSlowdown), bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksEventReasonSwThermalSlowdown), bool(r & n.nvmlClocksEventReasonSwPowerCap)]
+        return [time.time(), mhz, self.max_mhz] + flags
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if not out:
+            return None
+        f = [x.strip() for x in out.split(',')]
+        return [time.time(), float(f[0]), float(f[1])] + [x == 'Active' for x in f[2:6]]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([time.time()] + [x.strip() for x in out.split(',')])
+                row = self._sample_nvml() if self.nvml else self._sample_smi()
+                if row:
+                    self.rows.append(row)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag = True
         if not self.rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        rows = [r[1:] for r in self.rows]
-        inside = [r[1:] for r in self.rows if self.window[0] is not None and self.window[0] <= r[0] <= self.window[1]]
-        sm = sorted(float(r[0]) for r in rows)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == 'Active' for r in rows)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][1]), 'reasons': reasons,
-                'samples': len(sm), 'samples_in_timed_region': len(inside),
-                'note': 'sampled every 0.2 s from warm-up to the end of the device-timed and e2e loops (GPU busy throughout)'}
+        inside = [r for r in self.rows if self.window[0] is not None and self.window[0] <= r[0] <= self.window[1]]
+        use = inside or self.rows
+        sm = sorted(r[1] for r in use)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[3 + i] for r in use)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_min_mhz': sm[0], 'sm_max_mhz': self.rows[0][2], 'reasons': reasons,
+                'samples': len(self.rows), 'samples_in_timed_region': len(inside),
+                'source': 'nvml' if self.nvml else 'nvidia-smi',
+                'note': 'median/min/reasons over the samples taken inside the device-timed region '
+                        '(every %.0f ms from a host thread); all samples if the region held none'
+                        % (1e3 * (self.period if self.nvml else 0.2))}
 
 
 # --------------------------------------------------------------------------

@@ -76,6 +76,10 @@ int lmc_op_perm(const lmc_op* op, int* perm_host);
 /* OUT = K~ V  (SumMatrix.matvec, sum_matrix.py:31-32, over the whole tree)     */
 int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream);
 int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_host);
+/* Same product with V and OUT in the operator's own point order (sorted by output and grid cell:
+ * element i is point lmc_op_perm()[i] of the caller).  This is the layout the batched solver
+ * keeps its state in; every access is then coalesced.                                          */
+int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream);
 /* unit-testable stages.  Grid vectors are [P][D*m], output-major (likelihood.py:30):
  *   lmc_to_grid    G = W^T V      (WT.dot, ski.py:16)
  *   lmc_grid_mvm   GOUT = (sum_q B_q (x) T_q) GIN   (grid_kernel.py:126-136)

@@ -64,7 +64,10 @@ def launches(path, title, command):
 
 
 def full(path, title):
-    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if path.endswith('.csv'):
+        out = open(path).read()
+    else:
+        out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = rows_of(out)
     hdr, units = rows[0], rows[1]
     ik = hdr.index('Kernel Name')

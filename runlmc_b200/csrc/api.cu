@@ -115,7 +115,7 @@ int lmc_op_set_coreg_factors(lmc_op* op, const int* ranks_host, const double* A_
 long lmc_op_n(const lmc_op* op) { return op ? op->ps.n : -1; }
 long lmc_op_grid_cells(const lmc_op* op) { return op ? op->emb.cells : -1; }
 long lmc_op_embed_bins(const lmc_op* op) { return op ? op->emb.bins : -1; }
-int lmc_op_max_tile_points(const lmc_op* op) { return op ? op->ps.max_tile_pts : -1; }
+int lmc_op_max_tile_points(const lmc_op* op) { return op ? op->ps.max_tile_pts_8x8 : -1; }
 
 int lmc_op_perm(const lmc_op* op, int* perm_host) {
     LMC_REQUIRE(op && perm_host, "null argument");
@@ -129,6 +129,15 @@ int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, vo
     LMC_REQUIRE(V_dev != OUT_dev, "in-place product not supported");
     ColumnView cv;
     cv.in = V_dev; cv.out = OUT_dev; cv.ld = ld; cv.ncols = P;
+    return op_mvm(op, cv, (cudaStream_t)stream);
+}
+
+int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream) {
+    LMC_REQUIRE(op && V_dev && OUT_dev, "null argument");
+    LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
+    LMC_REQUIRE(V_dev != OUT_dev, "in-place product not supported");
+    ColumnView cv;
+    cv.in = V_dev; cv.out = OUT_dev; cv.ld = ld; cv.ncols = P; cv.sorted_in = cv.sorted_out = true;
     return op_mvm(op, cv, (cudaStream_t)stream);
 }
 

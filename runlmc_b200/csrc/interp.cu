@@ -6,16 +6,16 @@
 // multi_interpolant (approx/interpolation.py:56-116, 218-328, 119-176).
 //
 // Points are sorted once by (output, grid bin).  W^T v is then a segmented
-// reduction: one thread owns one bin, accumulates the 4^d per-tap partial sums
-// of its (contiguous) points in registers, partial sums are exchanged through
-// shared memory and each grid cell adds up the taps that land on it in a fixed
-// order -- deterministic and free of atomics.  Clamped stencils at the grid
-// edge accumulate onto the edge cell exactly like the reference's CSR `+=`
+// reduction over contiguous runs of points, staged in shared memory and summed
+// per grid cell in a fixed order -- deterministic and free of atomics (kernel
+// designs are described above each kernel).  Clamped stencils at the grid edge
+// accumulate onto the edge cell exactly like the reference's CSR `+=`
 // (interpolation.py:105-115).
 #include "interp.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace lmc {
@@ -83,26 +83,48 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
     for (long g = 0; g < n; ++g) ident = ident && perm[g] == (int)g;
     ps->identity = ident;
     if (ndim == 2) {
-        // population of every (16+3) x (16+3) bin window the tiled scatter kernel stages in shared memory
-        const int T = 16, B = T + 3;
-        int worst = 0;
-        for (int d = 0; d < D; ++d)
-            for (int cx0 = 0; cx0 < ps->m[0]; cx0 += T)
-                for (int cy0 = 0; cy0 < ps->m[1]; cy0 += T) {
-                    long cnt = 0;
-                    for (int bx = cx0; bx < cx0 + B && bx < ps->nb[0]; ++bx) {
-                        const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
-                        const int hi = std::min(cy0 + B, ps->nb[1]);
-                        cnt += start[base + hi] - start[base + cy0];
+        // population of every (TX+3) x (TY+3) bin window the tiled scatter kernels stage in shared memory
+        auto worst_window = [&](int TX, int TY) {
+            const int BX = TX + 3, BY = TY + 3;
+            long worst = 0;
+            for (int d = 0; d < D; ++d)
+                for (int cx0 = 0; cx0 < ps->m[0]; cx0 += TX)
+                    for (int cy0 = 0; cy0 < ps->m[1]; cy0 += TY) {
+                        long cnt = 0;
+                        for (int bx = cx0; bx < cx0 + BX && bx < ps->nb[0]; ++bx) {
+                            const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
+                            const int hi = std::min(cy0 + BY, ps->nb[1]);
+                            cnt += start[base + hi] - start[base + cy0];
+                        }
+                        worst = std::max(worst, cnt);
                     }
-                    worst = std::max<long>(worst, cnt);
+            return (int)worst;
+        };
+        ps->max_tile_pts_8x8 = worst_window(8, 8);
+        // population of every 16 x 16 tile of bins (no halo) the tiled gather kernel hands to one CTA
+        long worst = 0;
+        for (int d = 0; d < D; ++d)
+            for (int bx0 = 0; bx0 < ps->nb[0]; bx0 += 16)
+                for (int by0 = 0; by0 < ps->nb[1]; by0 += 16) {
+                    long cnt = 0;
+                    for (int bx = bx0; bx < bx0 + 16 && bx < ps->nb[0]; ++bx) {
+                        const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
+                        cnt += start[base + std::min(by0 + 16, ps->nb[1])] - start[base + by0];
+                    }
+                    worst = std::max(worst, cnt);
                 }
-        ps->max_tile_pts = worst;
+        ps->max_gather_tile_pts = (int)worst;
     }
     std::vector<int> si(n);
     std::vector<double> su(n);
     LMC_CHECK(cudaMalloc(&ps->perm, sizeof(int) * n));
     LMC_CHECK(cudaMemcpy(ps->perm, perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    if (!ident) {
+        std::vector<int> inv((size_t)n);
+        for (long g = 0; g < n; ++g) inv[perm[g]] = (int)g;
+        LMC_CHECK(cudaMalloc(&ps->iperm, sizeof(int) * n));
+        LMC_CHECK(cudaMemcpy(ps->iperm, inv.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
     for (int p = 0; p < ndim; ++p) {
         for (long g = 0; g < n; ++g) {
             si[g] = i0h[p][perm[g]];
@@ -122,6 +144,7 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
 
 void free_points(PointSet* ps) {
     cudaFree(ps->perm);
+    cudaFree(ps->iperm);
     for (int p = 0; p < 2; ++p) {
         cudaFree(ps->i0[p]);
         cudaFree(ps->u[p]);
@@ -156,17 +179,19 @@ __device__ __forceinline__ void keys_weights(double u, double* w) {
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+
 struct InterpArgs {
     const double* u0;
     const double* u1;
     const int* i00;
     const int* i01;
-    const int* perm;
+    const int* perm_in;    // sorted position -> index into the columns of `in` (nullptr: sorted order)
+    const int* perm_out;   // same for `out`
     const int* bin_start;
     const long* out_start;
     const double* in;
     double* out;
-    long ld;
+    long ld, ldo;          // column strides of in / out
     int ncols;
     const double* in_scale;
     const int* active;
@@ -176,7 +201,7 @@ struct InterpArgs {
     long grid_pitch;
     int D, m0, m1;
     long NB;
-    int nb1;
+    int nb0, nb1;
     int tiles, tiles1;
 };
 
@@ -187,204 +212,205 @@ __device__ __forceinline__ bool group_active(const InterpArgs& a, int c0, int cn
     return any;
 }
 
-// ---------------------------------------------------------------------------
-// 1-D scatter.  A CTA of 256 threads owns NBIN = 256/TPB consecutive bins of one
-// output (TPB = threads per bin, a power of two chosen from the point density so
-// that every thread has a few points) and the NBIN-3 cells whose stencils are
-// completely covered by them; it handles PT columns (PT/2 RHS pairs).  Points
-// stream through shared memory in coalesced chunks; each thread accumulates the
-// 4 per-tap partial sums of its share of its bin's points in registers, the TPB
-// partials are combined with a fixed-order shuffle tree, exchanged through
-// shared memory, and every cell adds up the (bin, tap) pairs that land on it in
-// a fixed order.  Deterministic, no atomics.
-// ---------------------------------------------------------------------------
-static const int kCap1 = 1024;
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::); }
 
-template <int PT, bool PERM>
-__global__ void __launch_bounds__(256) to_grid_1d_kernel(const InterpArgs a, int ltpb) {
-    __shared__ double s_u[kCap1];
-    __shared__ double s_v[PT][kCap1];  // reused for the per-bin partial sums (4*PT*NBIN <= PT*1024)
-    const int tpb = 1 << ltpb;
-    const int NBIN = blockDim.x >> ltpb;
-    const int TC = NBIN - 3;
+// Copies of the 2G columns of one pair group for one staged point, transposed on the way in to
+// v[re | im plane][point][pair] (pitch VP = G + 1 doubles: conflict-free for these strided stores and
+// for the lane-contiguous loads of the scatter loops).  Columns past the block are zero-filled.
+template <int G, int CAP>
+__device__ __forceinline__ void stage_point_values(double* v, int i, const double* gp, long ld, int ncol) {
+    constexpr int VP = G + 1;
+    double* dst = v + i * VP;
+#pragma unroll 8
+    for (int c = 0; c < ncol; ++c) cp_async8(dst + (c & 1) * (CAP * VP) + (c >> 1), gp + (long)c * ld);
+    for (int c = ncol; c < 2 * G; ++c) dst[(c & 1) * (CAP * VP) + (c >> 1)] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// The scatter kernels (W^T v) are "pair parallel": the lanes of a (part of a)
+// warp are G different RHS pairs working on the SAME grid bins / cells.  That
+// makes every weight load a shared-memory broadcast, every value load
+// v[point][pair] contiguous across lanes (conflict free), and gives all lanes of
+// a group the same control flow, whatever the number of points per bin.  (An
+// earlier cell-per-lane kernel was bound by shared-memory bank conflicts --
+// 2.1 wavefronts per ideal one in ncu -- and Poisson divergence.)
+// Every cell adds up its contributions in a fixed order: deterministic, no
+// atomics; clamped stencils at the grid edge accumulate onto the edge cell like
+// the reference's CSR `+=` (interpolation.py:105-115).
+// ---------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------
+// 1-D scatter.  A CTA owns NB = 256 / G consecutive bins of one output and the
+// NB - 3 cells whose stencils they cover, for one group of G pairs.  Thread
+// (bin, pair) accumulates the bin's 4 per-tap partial sums over the bin's
+// (contiguous) points, streamed through shared memory in chunks of CAP points;
+// partials are exchanged through shared memory and thread (cell, pair) adds the
+// (bin, tap) partials that land on its cell.
+// ---------------------------------------------------------------------------
+template <int G, int CAP>
+struct Scatter1Smem {
+    double2 w[CAP][2];            // Keys weights of the 4 taps
+    double v[2][CAP * (G + 1)];   // reused for the partial sums
+};
+
+template <int G, int CAP>
+__global__ void __launch_bounds__(256, 2) to_grid_1d_v3_kernel(const InterpArgs a) {
+    typedef Scatter1Smem<G, CAP> Smem;
+    constexpr int NBIN = 256 / G, TC = NBIN - 3, VP = G + 1;
+    static_assert(CAP <= 512 && 8 * NBIN * G <= 2 * CAP * VP, "staging / exchange layout");
+    extern __shared__ __align__(16) unsigned char smem_raw1[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw1);
+    const int tid = threadIdx.x;
     const int tile = blockIdx.x % a.tiles;
     const int d = blockIdx.x / a.tiles;
-    const int col0 = blockIdx.y * PT;
-    if (!group_active(a, col0, PT)) return;
+    const int grp = blockIdx.y;
+    const int col0 = 2 * G * grp;
+    if (!group_active(a, col0, 2 * G)) return;
+    const int ncol = min(2 * G, a.ncols - col0);
     const int m = a.m0;
-    const int c0 = tile * TC;
+    const int c0 = tile * TC;                       // first cell == first bin index (bin = i0 + 2)
     const int* bs = a.bin_start + (long)d * a.NB;
-    const int last_bin = min(c0 + TC + 2, m + 2);
-    const int lbin = threadIdx.x >> ltpb, sub = threadIdx.x & (tpb - 1);
-    const int my_bin = c0 + lbin;  // bin index = i0 + 2
+    const int last_bin = min(c0 + NBIN - 1, m + 2);
+    const int g = tid & (G - 1), lb = tid / G;
+    const int my_bin = c0 + lb;
     const bool has_bin = my_bin <= last_bin;
     const int pbeg = bs[c0], pend = bs[last_bin + 1];
     const int my_beg = has_bin ? bs[my_bin] : 0;
     const int my_end = has_bin ? bs[my_bin + 1] : 0;
-    double scale[PT];
+    double acc[4][2];
 #pragma unroll
-    for (int p = 0; p < PT; ++p)
-        scale[p] = (col0 + p < a.ncols) ? (a.in_scale ? a.in_scale[col0 + p] : 1.0) : 0.0;
-    double acc[4][PT];
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int p = 0; p < PT; ++p) acc[t][p] = 0.0;
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const double* vre = s.v[0] + g;
+    const double* vim = s.v[1] + g;
 
-    for (int chunk = pbeg; chunk < pend; chunk += kCap1) {
-        const int cnt = min(kCap1, pend - chunk);
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-            s_u[i] = a.u0[chunk + i];
-            const long src = PERM ? (long)a.perm[chunk + i] : (long)(chunk + i);
-#pragma unroll
-            for (int p = 0; p < PT; ++p)
-                s_v[p][i] = (col0 + p < a.ncols) ? a.in[(long)(col0 + p) * a.ld + src] : 0.0;
+    for (int chunk = pbeg; chunk < pend; chunk += CAP) {
+        const int cnt = min(CAP, pend - chunk);
+        for (int i = tid; i < cnt; i += 256) {
+            const int gi = chunk + i;
+            double w[4];
+            keys_weights(a.u0[gi], w);
+            s.w[i][0] = make_double2(w[0], w[1]);
+            s.w[i][1] = make_double2(w[2], w[3]);
+            const long src = a.perm_in ? (long)a.perm_in[gi] : (long)gi;
+            stage_point_values<G, CAP>(s.v[0], i, a.in + (long)col0 * a.ld + src, a.ld, ncol);
         }
+        cp_async_commit();
+        cp_async_wait_all();
         __syncthreads();
         const int lo = max(my_beg, chunk) - chunk, hi = min(my_end, chunk + cnt) - chunk;
-        // the bin's points are dealt round-robin to its TPB threads, aligned to the bin start
-        int first = lo + ((sub - (lo + chunk - my_beg)) & (tpb - 1));
-        for (int i = first; i < hi; i += tpb) {
-            double w[4];
-            keys_weights(s_u[i], w);
-#pragma unroll
-            for (int p = 0; p < PT; ++p) {
-                const double v = s_v[p][i];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t][p] = fma(w[t], v, acc[t][p]);
-            }
+#pragma unroll 2
+        for (int i = lo; i < hi; ++i) {
+            const double2 wa = s.w[i][0], wb = s.w[i][1];
+            const double vr = vre[i * VP], vi = vim[i * VP];
+            acc[0][0] = fma(wa.x, vr, acc[0][0]); acc[0][1] = fma(wa.x, vi, acc[0][1]);
+            acc[1][0] = fma(wa.y, vr, acc[1][0]); acc[1][1] = fma(wa.y, vi, acc[1][1]);
+            acc[2][0] = fma(wb.x, vr, acc[2][0]); acc[2][1] = fma(wb.x, vi, acc[2][1]);
+            acc[3][0] = fma(wb.y, vr, acc[3][0]); acc[3][1] = fma(wb.y, vi, acc[3][1]);
         }
         __syncthreads();
     }
-    // combine the TPB partials of a bin (fixed xor tree), apply the column scale
+    // exchange the per-bin partials: part[tap][re|im][bin][pair]
+    double* part = s.v[0];
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int p = 0; p < PT; ++p) {
-            double v = acc[t][p];
-            for (int o = 1; o < tpb; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[t][p] = v * scale[p];
-        }
-    double* sA = &s_v[0][0];
-    if (sub == 0) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int p = 0; p < PT; ++p) sA[(t * PT + p) * NBIN + lbin] = acc[t][p];
+    for (int t = 0; t < 4; ++t) {
+        part[((t * 2 + 0) * NBIN + lb) * G + g] = acc[t][0];
+        part[((t * 2 + 1) * NBIN + lb) * G + g] = acc[t][1];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < TC; c += blockDim.x) {
-        const int j = c0 + c;
-        if (j >= m) break;
-        double sum[PT];
-#pragma unroll
-        for (int p = 0; p < PT; ++p) sum[p] = 0.0;
+    const int j = c0 + lb;                          // thread (cell lb, pair g)
+    const int pair = grp * G + g;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    if (lb < TC && j < m && pair < npairs_tot) {
+        const int cA = 2 * pair, cB = 2 * pair + 1;
+        if (a.active && !a.active[cA] && !(cB < a.ncols && a.active[cB])) return;
+        double sr = 0.0, si = 0.0;
         const int ilo = max(j - 2, -2), ihi = min(j + 1, m);
         for (int i0 = ilo; i0 <= ihi; ++i0) {
-            const int lb = i0 + 2 - c0;
+            const int b = i0 + 2 - c0;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 if (clampi(i0 - 1 + t, 0, m - 1) == j) {
-#pragma unroll
-                    for (int p = 0; p < PT; ++p) sum[p] += sA[(t * PT + p) * NBIN + lb];
+                    sr += part[((t * 2 + 0) * NBIN + b) * G + g];
+                    si += part[((t * 2 + 1) * NBIN + b) * G + g];
                 }
             }
         }
-#pragma unroll
-        for (int p = 0; p < PT; p += 2) {
-            const int pair = (col0 + p) >> 1;
-            if (col0 + p < a.ncols)
-                a.G[((long)pair * a.D + d) * a.grid_pitch + j] = make_double2(sum[p], (p + 1 < PT) ? sum[p + 1] : 0.0);
+        double s0 = 1.0, s1 = 1.0;   // W^T (v s) = s W^T v: the column scale is applied to the sums
+        if (a.in_scale) {
+            s0 = a.in_scale[cA];
+            s1 = (cB < a.ncols) ? a.in_scale[cB] : 0.0;
         }
-    }
-}
-
-// 1-D gather: the TPB threads of a bin keep the bin's 4 taps of PT columns in
-// registers and walk their share of the bin's points; results are staged in
-// shared memory so the global stores (and the fused  + noise * in  epilogue) are
-// coalesced.
-template <int PT, bool PERM>
-__global__ void __launch_bounds__(256) from_grid_1d_kernel(const InterpArgs a, int ltpb) {
-    __shared__ double s_u[kCap1];
-    __shared__ double s_o[PT][kCap1];
-    const int tpb = 1 << ltpb;
-    const int NBIN = blockDim.x >> ltpb;
-    const int tile = blockIdx.x % a.tiles;
-    const int d = blockIdx.x / a.tiles;
-    const int col0 = blockIdx.y * PT;
-    if (!group_active(a, col0, PT)) return;
-    const int m = a.m0;
-    const int b0 = tile * NBIN;
-    const int* bs = a.bin_start + (long)d * a.NB;
-    const int last_bin = min(b0 + NBIN - 1, m + 2);
-    const int lbin = threadIdx.x >> ltpb, sub = threadIdx.x & (tpb - 1);
-    const int my_bin = b0 + lbin;
-    const bool has_bin = my_bin <= last_bin;
-    const int pbeg = bs[b0], pend = bs[last_bin + 1];
-    const int my_beg = has_bin ? bs[my_bin] : 0;
-    const int my_end = has_bin ? bs[my_bin + 1] : 0;
-    double tap[4][PT];
-    if (has_bin && my_end > my_beg) {
-        const int i0 = my_bin - 2;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int cell = clampi(i0 - 1 + t, 0, m - 1);
-#pragma unroll
-            for (int p = 0; p < PT; p += 2) {
-                const int pair = (col0 + p) >> 1;
-                cplx g = make_double2(0.0, 0.0);
-                if (col0 + p < a.ncols) g = a.Gc[((long)pair * a.D + d) * a.grid_pitch + cell];
-                tap[t][p] = g.x;
-                if (p + 1 < PT) tap[t][p + 1] = g.y;
-            }
-        }
-    }
-    const double nz = a.noise ? a.noise[d] : 0.0;
-    for (int chunk = pbeg; chunk < pend; chunk += kCap1) {
-        const int cnt = min(kCap1, pend - chunk);
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_u[i] = a.u0[chunk + i];
-        __syncthreads();
-        const int lo = max(my_beg, chunk) - chunk, hi = min(my_end, chunk + cnt) - chunk;
-        int first = lo + ((sub - (lo + chunk - my_beg)) & (tpb - 1));
-        for (int i = first; i < hi; i += tpb) {
-            double w[4];
-            keys_weights(s_u[i], w);
-#pragma unroll
-            for (int p = 0; p < PT; ++p) {
-                double o = 0.0;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) o = fma(w[t], tap[t][p], o);
-                s_o[p][i] = o;
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const long dst = PERM ? (long)a.perm[chunk + i] : (long)(chunk + i);
-#pragma unroll
-            for (int p = 0; p < PT; ++p) {
-                const int c = col0 + p;
-                if (c >= a.ncols) continue;
-                if (a.active && !a.active[c]) continue;
-                double o = s_o[p][i];
-                if (a.noise) {
-                    const double sc = a.in_scale ? a.in_scale[c] : 1.0;
-                    o = fma(nz, a.in[(long)c * a.ld + dst] * sc, o);
-                }
-                a.out[(long)c * a.ld + dst] = o;
-            }
-        }
-        __syncthreads();
+        a.G[((long)pair * a.D + d) * a.grid_pitch + j] = make_double2(sr * s0, si * s1);
     }
 }
 
 // ---------------------------------------------------------------------------
-// 2-D scatter: CTA owns a TX x TY tile of cells of one output and the
-// (TX+3) x (TY+3) bins around it; one thread per bin, one RHS pair per CTA.
+// 1-D gather: one thread per point (sorted order: neighbouring lanes read the
+// same or neighbouring cells, which L1 serves), looping over the RHS pairs so
+// the weights are computed once per point.  Epilogue: + noise_d * in.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) from_grid_1d_v3_kernel(const InterpArgs a, int pairs_per_cta) {
+    const int d = blockIdx.y;
+    const long i = a.out_start[d] + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.out_start[d + 1]) return;
+    const int m = a.m0;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    double w[4];
+    keys_weights(a.u0[i], w);
+    const int i0 = a.i00[i];
+    int cell[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) cell[t] = clampi(i0 - 1 + t, 0, m - 1);
+    const long si = a.perm_in ? (long)a.perm_in[i] : i;
+    const long so = a.perm_out ? (long)a.perm_out[i] : i;
+    const double nz = a.noise ? a.noise[d] : 0.0;
+    const int pair0 = blockIdx.z * pairs_per_cta;
+    const int pair1 = min(npairs_tot, pair0 + pairs_per_cta);
+    const cplx* gbase = a.Gc + (long)d * a.grid_pitch;
+    const long pstride = (long)a.D * a.grid_pitch;
+#pragma unroll 2
+    for (int pair = pair0; pair < pair1; ++pair) {
+        const int cA = 2 * pair, cB = cA + 1;
+        const bool hasB = cB < a.ncols;
+        const bool actA = !a.active || a.active[cA];
+        const bool actB = hasB && (!a.active || a.active[cB]);
+        if (!actA && !actB) continue;
+        const cplx* gp = gbase + pair * pstride;
+        const cplx v0 = __ldg(gp + cell[0]), v1 = __ldg(gp + cell[1]);
+        const cplx v2 = __ldg(gp + cell[2]), v3 = __ldg(gp + cell[3]);
+        double inA = 0.0, inB = 0.0;
+        if (a.noise) {
+            if (actA) inA = a.in[(long)cA * a.ld + si];
+            if (actB) inB = a.in[(long)cB * a.ld + si];
+            if (a.in_scale) { inA *= a.in_scale[cA]; if (hasB) inB *= a.in_scale[cB]; }
+        }
+        double oA = fma(w[3], v3.x, fma(w[2], v2.x, fma(w[1], v1.x, w[0] * v0.x)));
+        double oB = fma(w[3], v3.y, fma(w[2], v2.y, fma(w[1], v1.y, w[0] * v0.y)));
+        if (a.noise) { oA = fma(nz, inA, oA); oB = fma(nz, inB, oB); }
+        if (actA) a.out[(long)cA * a.ldo + so] = oA;
+        if (actB) a.out[(long)cB * a.ldo + so] = oB;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 2-D scatter, fallback for badly clustered points (no per-tile capacity):
+// CTA owns a 16 x 16 tile of cells of one output and the 19 x 19 bins around
+// it; one thread per bin, one RHS pair per CTA; per-bin 4x4 tap partials are
+// exchanged through shared memory.
 // ---------------------------------------------------------------------------
 static const int kTX = 16, kTY = 16;
 static const int kBX = kTX + 3, kBY = kTY + 3;  // 19 x 19 = 361 bins
 
-template <bool PERM>
 __global__ void __launch_bounds__(384) to_grid_2d_kernel(const InterpArgs a) {
     extern __shared__ double sA[];  // [16 taps][2][kBX*kBY]
     const int tile = blockIdx.x % a.tiles;
@@ -413,7 +439,7 @@ __global__ void __launch_bounds__(384) to_grid_2d_kernel(const InterpArgs a) {
             double wx[4], wy[4];
             keys_weights(a.u0[i], wx);
             keys_weights(a.u1[i], wy);
-            const long src = PERM ? (long)a.perm[i] : (long)i;
+            const long src = a.perm_in ? (long)a.perm_in[i] : (long)i;
             const double v0 = a.in[(long)col0 * a.ld + src] * s0;
             const double v1 = c1 ? a.in[(long)(col0 + 1) * a.ld + src] * s1 : 0.0;
 #pragma unroll
@@ -461,106 +487,52 @@ __global__ void __launch_bounds__(384) to_grid_2d_kernel(const InterpArgs a) {
     }
 }
 
-// 2-D gather: one thread per point (sorted order => neighbouring threads read
-// neighbouring cells), one RHS pair per thread.
-template <bool PERM>
-__global__ void __launch_bounds__(128) from_grid_2d_kernel(const InterpArgs a) {
-    const int d = blockIdx.y;
-    const int pair = blockIdx.z;
-    const int col0 = pair * 2;
-    if (!group_active(a, col0, 2)) return;
-    const long i = a.out_start[d] + (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.out_start[d + 1]) return;
-    const int mx = a.m0, my = a.m1;
-    double wx[4], wy[4];
-    keys_weights(a.u0[i], wx);
-    keys_weights(a.u1[i], wy);
-    const int ix0 = a.i00[i] - 1, iy0 = a.i01[i] - 1;
-    const cplx* g = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
-    int cy[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) cy[j] = clampi(iy0 + j, 0, my - 1);
-    double o0 = 0.0, o1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const long row = (long)clampi(ix0 + k, 0, mx - 1) * my;
-        double r0 = 0.0, r1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const cplx v = __ldg(&g[row + cy[j]]);
-            r0 = fma(wy[j], v.x, r0);
-            r1 = fma(wy[j], v.y, r1);
-        }
-        o0 = fma(wx[k], r0, o0);
-        o1 = fma(wx[k], r1, o1);
-    }
-    const long dst = PERM ? (long)a.perm[i] : i;
-    const double nz = a.noise ? a.noise[d] : 0.0;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const int c = col0 + p;
-        if (c >= a.ncols) continue;
-        if (a.active && !a.active[c]) continue;
-        double o = p ? o1 : o0;
-        if (a.noise) {
-            const double sc = a.in_scale ? a.in_scale[c] : 1.0;
-            o = fma(nz, a.in[(long)c * a.ld + dst] * sc, o);
-        }
-        a.out[(long)c * a.ld + dst] = o;
-    }
-}
-
 // ---------------------------------------------------------------------------
-// 2-D scatter, v2: "cell-owner gather".  A CTA owns a 16x16 tile of cells and
-// stages the points of the 19x19 surrounding bins in shared memory together
-// with their 4+4 Keys weights (computed once per point, balanced over threads,
-// reused for every RHS pair the CTA loops over).  Each thread then owns one
-// cell and sums, in fixed order, the contributions of the points in its 4x4
-// neighbouring bins: every point is visited with exactly the one (kx, ky) tap
-// that lands on the cell.  Summing 16 bins per thread evens out the Poisson
-// imbalance of sparse bins (thread-per-bin wastes ~3.4x of the lanes at 1.5
-// points per bin).  Deterministic, no atomics.
+// 2-D scatter, "pair-parallel strips".  Thread (strip, pair): a strip is 4 cells
+// consecutive in x.  A CTA stages the points of the (TX+3) x (TY+3) bins around
+// its TX x TY tile of cells once (weights) and their values once per group of G
+// pairs.  One visit of a point serves up to 4 cells (7 visits per point instead
+// of 16 for cell-per-thread ownership), x taps are compile-time constants of the
+// unrolled bin-row / bin loops.
 // ---------------------------------------------------------------------------
-static const int kCap2 = 800;            // staged points per tile (host checks PointSet::max_tile_pts)
-static const int kCap2P = kCap2 + 4;     // row pitch: shifts the 4 tap rows onto different banks
-
-struct Tile2Smem {
-    double wx[4][kCap2P];
-    double wy[4][kCap2P];
-    double2 v[2][2][kCap2];  // [buffer][pair of the pass][point]: double-buffered cp.async target
-    int src[kCap2];
-    int bin[kBX][kBY + 1];   // local offsets of every bin of the window (+ end of row)
-    int row_beg[kBX];        // global sorted index of the first point of each bin row
-    int row_off[kBX + 1];    // local prefix
+template <int G, int TX, int TY, int CAP>
+struct Tile3Smem {
+    static const int BX = TX + 3, BY = TY + 3;
+    double wx[4][CAP];
+    double wy[4][CAP];
+    double v[2][CAP * (G + 1)];   // [re | im][point][pair]
+    int src[CAP];
+    int bin[BX][BY + 1];          // local offset of every bin of the window (+ end of row)
+    int row_beg[BX];
+    int row_off[BX + 1];
 };
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-
-template <bool PERM>
-__global__ void __launch_bounds__(256, 2) to_grid_2d_v2_kernel(const InterpArgs a, int pairs_per_cta) {
-    extern __shared__ __align__(16) unsigned char smem_raw2[];
-    Tile2Smem& s = *reinterpret_cast<Tile2Smem*>(smem_raw2);
+template <int G, int TX, int TY, int CAP>
+__global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs a, int groups_per_cta) {
+    typedef Tile3Smem<G, TX, TY, CAP> Smem;
+    static_assert((TX / 4) * TY * G == 256, "one thread per (strip, pair)");
+    static_assert(CAP <= 512, "two staged points per thread");
+    constexpr int BX = Smem::BX, BY = Smem::BY, VP = G + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw3[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw3);
     const int tile = blockIdx.x % a.tiles;
     const int d = blockIdx.x / a.tiles;
-    const int pair0 = blockIdx.y * pairs_per_cta;
     const int npairs_tot = (a.ncols + 1) >> 1;
+    const int ngroups = (npairs_tot + G - 1) / G;
+    const int grp0 = blockIdx.y * groups_per_cta;
+    const int grp1 = min(ngroups, grp0 + groups_per_cta);
     const int mx = a.m0, my = a.m1;
     const int tx = tile / a.tiles1, ty = tile % a.tiles1;
-    const int cx0 = tx * kTX, cy0 = ty * kTY;
+    const int cx0 = tx * TX, cy0 = ty * TY;
     const int* bs = a.bin_start + (long)d * a.NB;
     const int tid = threadIdx.x;
 
-    // ---- window geometry ----
-    if (tid < kBX) {
+    // ---- window geometry (bin index = i0 + 2; cell j collects from bins j .. j+3) ----
+    if (tid < BX) {
         const int bx = cx0 + tid;
         int beg = 0, end = 0;
         if (bx <= mx + 2) {
-            const int by_hi = min(cy0 + kBY, my + 3);
+            const int by_hi = min(cy0 + BY, my + 3);
             beg = bs[(long)bx * a.nb1 + cy0];
             end = bs[(long)bx * a.nb1 + by_hi];
         }
@@ -570,11 +542,11 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v2_kernel(const InterpArgs 
     __syncthreads();
     if (tid == 0) {
         s.row_off[0] = 0;
-        for (int r = 0; r < kBX; ++r) s.row_off[r + 1] += s.row_off[r];
+        for (int r = 0; r < BX; ++r) s.row_off[r + 1] += s.row_off[r];
     }
     __syncthreads();
-    for (int i = tid; i < kBX * (kBY + 1); i += blockDim.x) {
-        const int r = i / (kBY + 1), c = i % (kBY + 1);
+    for (int i = tid; i < BX * (BY + 1); i += blockDim.x) {
+        const int r = i / (BY + 1), c = i % (BY + 1);
         const int bx = cx0 + r;
         int off = s.row_off[r + 1];
         if (bx <= mx + 2) {
@@ -583,116 +555,128 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v2_kernel(const InterpArgs 
         }
         s.bin[r][c] = off;
     }
-    const int npts = s.row_off[kBX];
-    const int npass = (min(pairs_per_cta, npairs_tot - pair0) + 1) >> 1;
-
-    // stage the RHS values of pass `ps` (two pairs = four columns) with cp.async; columns past the
-    // end of the block are zero-filled by ordinary stores
-    auto stage = [&](int ps, int buf) {
-        const int pair = pair0 + 2 * ps;
-        for (int i = tid; i < npts; i += blockDim.x) {
-            const long src = s.src[i];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int c = 2 * pair + h;
-                double* dst = reinterpret_cast<double*>(&s.v[buf][h >> 1][i]) + (h & 1);
-                if (c < a.ncols && (h < 2 || 2 * ps + 1 < pairs_per_cta)) cp_async8(dst, a.in + (long)c * a.ld + src);
-                else *dst = 0.0;
-            }
-        }
-        cp_async_commit();
-    };
-
-    // ---- per-point weights (once per CTA) ----
+    const int npts = s.row_off[BX];
+    // ---- per-point weights, once per CTA ----
     for (int i = tid; i < npts; i += blockDim.x) {
         int r = 0;
         while (i >= s.row_off[r + 1]) ++r;
-        const int g = s.row_beg[r] + (i - s.row_off[r]);
+        const int gidx = s.row_beg[r] + (i - s.row_off[r]);
         double wx[4], wy[4];
-        keys_weights(a.u0[g], wx);
-        keys_weights(a.u1[g], wy);
+        keys_weights(a.u0[gidx], wx);
+        keys_weights(a.u1[gidx], wy);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { s.wx[k][i] = wx[k]; s.wy[k][i] = wy[k]; }
-        s.src[i] = PERM ? a.perm[g] : g;
+        s.src[i] = a.perm_in ? a.perm_in[gidx] : gidx;
     }
     __syncthreads();
-    if (npass > 0) stage(0, 0);
 
-    const int lcx = tid / kTY, lcy = tid % kTY;
-    const int jx = cx0 + lcx, jy = cy0 + lcy;
-    const bool in_grid = jx < mx && jy < my;
-    const bool interior = jx >= 1 && jx <= mx - 2 && jy >= 1 && jy <= my - 2;
+    const int i_a = tid, i_b = tid + 256;   // the (up to) two staged points this thread copies
+    const long src_a = i_a < npts ? s.src[i_a] : 0, src_b = i_b < npts ? s.src[i_b] : 0;
+    const int g = tid & (G - 1);
+    const int strip = tid / G;
+    const int sy = strip % TY, sx = strip / TY;
+    const int jx0 = cx0 + 4 * sx, jy = cy0 + sy;
+    const bool in_grid = jx0 < mx && jy < my;
+    const bool interior = jx0 >= 1 && jx0 + 3 <= mx - 2 && jy >= 1 && jy <= my - 2;
+    const double* vre = s.v[0] + g;
+    const double* vim = s.v[1] + g;
 
-    for (int ps = 0; ps < npass; ++ps) {
-        const int buf = ps & 1;
-        const int pair = pair0 + 2 * ps;
-        const bool second = (2 * ps + 1 < pairs_per_cta) && (pair + 1 < npairs_tot);
-        cp_async_wait_all();
-        __syncthreads();                       // pass ps is staged; every thread finished pass ps-1
-        if (ps + 1 < npass) stage(ps + 1, buf ^ 1);   // overlaps with the gather below
-        if (!in_grid || !group_active(a, 2 * pair, second ? 4 : 2)) continue;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const double2* va_ = s.v[buf][0];
-        const double2* vb_ = s.v[buf][1];
-        if (interior) {
+    for (int grp = grp0; grp < grp1; ++grp) {
+        const int col0 = 2 * G * grp;
+        const bool live = group_active(a, col0, 2 * G);      // uniform over the CTA
+        if (live) {
+            const int ncol = min(2 * G, a.ncols - col0);
+            const double* gp = a.in + (long)col0 * a.ld;
+            if (i_a < npts) stage_point_values<G, CAP>(s.v[0], i_a, gp + src_a, a.ld, ncol);
+            if (i_b < npts) stage_point_values<G, CAP>(s.v[0], i_b, gp + src_b, a.ld, ncol);
+            cp_async_commit();
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        const int pair = grp * G + g;
+        if (live && in_grid && pair < npairs_tot) {
+            double acc[4][2];
 #pragma unroll
-            for (int aa = 0; aa < 4; ++aa) {
-                const int r = lcx + aa;          // bin row i0x = jx - 2 + aa  ->  tap kx = 3 - aa
-                const double* wxr = s.wx[3 - aa];
-                // the 4 bins (r, lcy..lcy+3) are one contiguous run of points; ky from the bin a point is in
-                const int b0 = s.bin[r][lcy], b1 = s.bin[r][lcy + 1], b2 = s.bin[r][lcy + 2];
-                const int b3 = s.bin[r][lcy + 3], b4 = s.bin[r][lcy + 4];
-                for (int i = b0; i < b4; ++i) {
-                    const int ky = 3 - ((i >= b1) + (i >= b2) + (i >= b3));
-                    const double w = wxr[i] * s.wy[ky][i];
-                    const double2 va = va_[i], vb = vb_[i];
-                    acc[0] = fma(w, va.x, acc[0]);
-                    acc[1] = fma(w, va.y, acc[1]);
-                    acc[2] = fma(w, vb.x, acc[2]);
-                    acc[3] = fma(w, vb.y, acc[3]);
-                }
-            }
-        } else {
-            // grid-edge cell: clamped taps of several bins / several taps of one bin land here
-            const int xlo = max(jx - 2, -2), xhi = min(jx + 1, mx);
-            const int ylo = max(jy - 2, -2), yhi = min(jy + 1, my);
-            for (int ix = xlo; ix <= xhi; ++ix) {
-                const int r = ix + 2 - cx0;
-                for (int iy = ylo; iy <= yhi; ++iy) {
-                    const int c = iy + 2 - cy0;
-                    for (int i = s.bin[r][c]; i < s.bin[r][c + 1]; ++i) {
-                        double wxs = 0.0, wys = 0.0;
+            for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = 0.0;
+            if (interior) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (clampi(ix - 1 + k, 0, mx - 1) == jx) wxs += s.wx[k][i];
-                            if (clampi(iy - 1 + k, 0, my - 1) == jy) wys += s.wy[k][i];
+                for (int aa = 0; aa < 7; ++aa) {
+                    // bin row 4 sx + aa: cell c of the strip takes x tap c - aa + 3 from it
+                    const int* brow = &s.bin[4 * sx + aa][sy];
+                    int i = brow[0];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {   // bin (row, sy + b) feeds cell jy with y tap 3 - b
+                        const int iend = brow[b + 1];
+                        const double* wyp = s.wy[3 - b];
+#pragma unroll 1
+                        for (; i < iend; ++i) {
+                            const double wyv = wyp[i];
+                            const double t0 = wyv * vre[i * VP], t1 = wyv * vim[i * VP];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const int kx = c - aa + 3;
+                                if (kx >= 0 && kx <= 3) {
+                                    const double wxv = s.wx[kx][i];
+                                    acc[c][0] = fma(wxv, t0, acc[c][0]);
+                                    acc[c][1] = fma(wxv, t1, acc[c][1]);
+                                }
+                            }
                         }
-                        const double w = wxs * wys;
-                        const double2 va = va_[i], vb = vb_[i];
-                        acc[0] = fma(w, va.x, acc[0]);
-                        acc[1] = fma(w, va.y, acc[1]);
-                        acc[2] = fma(w, vb.x, acc[2]);
-                        acc[3] = fma(w, vb.y, acc[3]);
                     }
                 }
-            }
-        }
-        if (a.in_scale) {   // W^T (v s) = s W^T v: the column scale is applied to the sums
+            } else {
+                // strip touching the grid edge: clamped taps of several bins / several taps of one bin
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                const int c = 2 * pair + h;
-                if (c < a.ncols) acc[h] *= a.in_scale[c];
+                for (int c = 0; c < 4; ++c) {
+                    const int jx = jx0 + c;
+                    if (jx >= mx) continue;
+                    const int xlo = max(jx - 2, -2), xhi = min(jx + 1, mx);
+                    const int ylo = max(jy - 2, -2), yhi = min(jy + 1, my);
+                    double a0 = 0.0, a1 = 0.0;
+                    for (int ix = xlo; ix <= xhi; ++ix) {
+                        const int r = ix + 2 - cx0;
+                        for (int iy = ylo; iy <= yhi; ++iy) {
+                            const int cc = iy + 2 - cy0;
+#pragma unroll 1
+                            for (int i = s.bin[r][cc]; i < s.bin[r][cc + 1]; ++i) {
+                                double wxs = 0.0, wys = 0.0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (clampi(ix - 1 + k, 0, mx - 1) == jx) wxs += s.wx[k][i];
+                                    if (clampi(iy - 1 + k, 0, my - 1) == jy) wys += s.wy[k][i];
+                                }
+                                const double w = wxs * wys;
+                                a0 = fma(w, vre[i * VP], a0);
+                                a1 = fma(w, vim[i * VP], a1);
+                            }
+                        }
+                    }
+                    acc[c][0] = a0;
+                    acc[c][1] = a1;
+                }
+            }
+            const int cA = 2 * pair, cB = 2 * pair + 1;
+            const bool act = !a.active || a.active[cA] || (cB < a.ncols && a.active[cB]);
+            if (act) {
+                double s0 = 1.0, s1 = 1.0;   // W^T (v s) = s W^T v: the column scale is applied to the sums
+                if (a.in_scale) {
+                    s0 = a.in_scale[cA];
+                    s1 = (cB < a.ncols) ? a.in_scale[cB] : 0.0;
+                }
+                cplx* gp = a.G + ((long)pair * a.D + d) * a.grid_pitch + jy;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (jx0 + c < mx) gp[(long)(jx0 + c) * my] = make_double2(acc[c][0] * s0, acc[c][1] * s1);
             }
         }
-        const long cell = (long)jx * my + jy;
-        a.G[((long)pair * a.D + d) * a.grid_pitch + cell] = make_double2(acc[0], acc[1]);
-        if (second) a.G[((long)(pair + 1) * a.D + d) * a.grid_pitch + cell] = make_double2(acc[2], acc[3]);
+        __syncthreads();   // every thread is done with this group's values
     }
 }
 
-// 2-D gather, v2: one thread per point loops over the RHS pairs of its group, so the
-// 4+4 weights and the 16 clamped cell offsets are computed once per point.
-template <bool PERM>
+// ---------------------------------------------------------------------------
+// 2-D gather, fallback without a per-tile capacity: one thread per point loops
+// over the RHS pairs of its group and reads the 16 cells through L1/L2.
+// ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) from_grid_2d_v2_kernel(const InterpArgs a, int pairs_per_cta) {
     const int d = blockIdx.y;
     const long i = a.out_start[d] + (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -710,7 +694,8 @@ __global__ void __launch_bounds__(128) from_grid_2d_v2_kernel(const InterpArgs a
         cy[j] = clampi(iy0 + j, 0, my - 1);
         row[j] = (long)clampi(ix0 + j, 0, mx - 1) * my;
     }
-    const long dst = PERM ? (long)a.perm[i] : i;
+    const long si = a.perm_in ? (long)a.perm_in[i] : i;
+    const long so = a.perm_out ? (long)a.perm_out[i] : i;
     const double nz = a.noise ? a.noise[d] : 0.0;
     const int pair0 = blockIdx.z * pairs_per_cta;
     for (int pp = 0; pp < pairs_per_cta; ++pp) {
@@ -740,37 +725,219 @@ __global__ void __launch_bounds__(128) from_grid_2d_v2_kernel(const InterpArgs a
             double o = p ? o1 : o0;
             if (a.noise) {
                 const double sc = a.in_scale ? a.in_scale[c] : 1.0;
-                o = fma(nz, a.in[(long)c * a.ld + dst] * sc, o);
+                o = fma(nz, a.in[(long)c * a.ld + si] * sc, o);
             }
-            a.out[(long)c * a.ld + dst] = o;
+            a.out[(long)c * a.ldo + so] = o;
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// host launchers
+// 2-D gather with the cells staged in shared memory.  A CTA owns the points of a
+// TB x TB tile of bins of one output (<= 512 points, two per thread) and the
+// (TB+3)^2 cells their stencils touch; the cells of GP pairs at a time are copied
+// in with cp.async (double buffered: the copies of the next pass overlap the
+// arithmetic of this one), so the 16 taps per point and pair are shared-memory
+// reads instead of L1 misses served by L2 (ncu on the L1 variant: 86 % of the
+// stalls were waits on those loads, L2 -> SM traffic ~7x the cell data).
 // ---------------------------------------------------------------------------
-// threads per bin of the 1-D kernels: keep ~4 points per thread at the average density
-static int threads_per_bin_log2(const PointSet& ps) {
-    const double density = (double)ps.n / ((double)ps.D * ps.m[0]);
-    int l = 0;
-    while (l < 5 && density > 4.0 * (1 << l)) ++l;
-    return l;
+template <int GP, int TB>
+struct Gather3Smem {
+    static const int W = TB + 3;
+    cplx cell[2][GP][W * W];
+    int row_beg[TB];
+    int row_off[TB + 1];
+};
+
+template <int GP, int TB>
+__global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArgs a, int passes_per_cta) {
+    typedef Gather3Smem<GP, TB> Smem;
+    constexpr int W = Smem::W;
+    extern __shared__ __align__(16) unsigned char smem_raw4[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw4);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x % a.tiles;
+    const int d = blockIdx.x / a.tiles;
+    const int mx = a.m0, my = a.m1;
+    const int BX0 = (tile / a.tiles1) * TB, BY0 = (tile % a.tiles1) * TB;   // first bin (bin = i0 + 2)
+    const int X0 = BX0 - 3, Y0 = BY0 - 3;                                   // first cell of the window
+    const int* bs = a.bin_start + (long)d * a.NB;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    const int pair_lo = blockIdx.y * passes_per_cta * GP;
+    const int pair_hi = min(npairs_tot, pair_lo + passes_per_cta * GP);
+    if (tid < TB) {
+        const int bx = BX0 + tid;
+        int beg = 0, end = 0;
+        if (bx < a.nb0) {
+            beg = bs[(long)bx * a.nb1 + BY0];
+            end = bs[(long)bx * a.nb1 + min(BY0 + TB, a.nb1)];
+        }
+        s.row_beg[tid] = beg;
+        s.row_off[tid + 1] = end - beg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s.row_off[0] = 0;
+        for (int r = 0; r < TB; ++r) s.row_off[r + 1] += s.row_off[r];
+    }
+    __syncthreads();
+    const int npts = s.row_off[TB];
+    if (npts == 0) return;
+
+    auto stage = [&](int pbase, int buf) {
+        for (int p = 0; p < GP; ++p) {
+            const int pair = pbase + p;
+            if (pair >= pair_hi) break;
+            if (!group_active(a, 2 * pair, 2)) continue;
+            const cplx* gsl = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
+            for (int c = tid; c < W * W; c += 256) {
+                const int x = c / W, y = c - x * W;
+                const int gx = X0 + x, gy = Y0 + y;
+                if (gx >= 0 && gx < mx && gy >= 0 && gy < my) cp_async16(&s.cell[buf][p][c], gsl + (long)gx * my + gy);
+            }
+        }
+        cp_async_commit();
+    };
+    stage(pair_lo, 0);
+
+    // ---- this thread's (up to) two points ----
+    double wx[2][4], wy[2][4];
+    int off[2][4], oy[2][4];
+    long si[2], so[2];
+    bool have[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int li = tid + 256 * q;
+        have[q] = li < npts;
+        si[q] = so[q] = 0;
+        if (have[q]) {
+            int r = 0;
+            while (li >= s.row_off[r + 1]) ++r;
+            const long gi = s.row_beg[r] + (li - s.row_off[r]);
+            keys_weights(a.u0[gi], wx[q]);
+            keys_weights(a.u1[gi], wy[q]);
+            const int ix0 = a.i00[gi] - 1, iy0 = a.i01[gi] - 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                off[q][k] = (clampi(ix0 + k, 0, mx - 1) - X0) * W;
+                oy[q][k] = clampi(iy0 + k, 0, my - 1) - Y0;
+            }
+            si[q] = a.perm_in ? (long)a.perm_in[gi] : gi;
+            so[q] = a.perm_out ? (long)a.perm_out[gi] : gi;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { wx[q][k] = wy[q][k] = 0.0; off[q][k] = oy[q][k] = 0; }
+        }
+    }
+    const double nz = a.noise ? a.noise[d] : 0.0;
+
+    int buf = 0;
+    for (int pbase = pair_lo; pbase < pair_hi; pbase += GP, buf ^= 1) {
+        if (pbase + GP < pair_hi) { stage(pbase + GP, buf ^ 1); cp_async_wait_1(); }
+        else cp_async_wait_all();
+        __syncthreads();
+#pragma unroll 1
+        for (int p = 0; p < GP; ++p) {
+            const int pair = pbase + p;
+            if (pair >= pair_hi) break;
+            const int cA = 2 * pair, cB = cA + 1;
+            const bool hasB = cB < a.ncols;
+            const bool actA = !a.active || a.active[cA];
+            const bool actB = hasB && (!a.active || a.active[cB]);
+            if (!actA && !actB) continue;
+            const cplx* cl = s.cell[buf][p];
+            const double scA = a.in_scale ? a.in_scale[cA] : 1.0;
+            const double scB = (a.in_scale && hasB) ? a.in_scale[cB] : 1.0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!have[q]) continue;
+                double inA = 0.0, inB = 0.0;
+                if (a.noise) {
+                    if (actA) inA = a.in[(long)cA * a.ld + si[q]] * scA;
+                    if (actB) inB = a.in[(long)cB * a.ld + si[q]] * scB;
+                }
+                double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const cplx v = cl[off[q][k] + oy[q][j]];
+                        r0 = fma(wy[q][j], v.x, r0);
+                        r1 = fma(wy[q][j], v.y, r1);
+                    }
+                    o0 = fma(wx[q][k], r0, o0);
+                    o1 = fma(wx[q][k], r1, o1);
+                }
+                if (a.noise) { o0 = fma(nz, inA, o0); o1 = fma(nz, inB, o1); }
+                if (actA) a.out[(long)cA * a.ldo + so[q]] = o0;
+                if (actB) a.out[(long)cB * a.ldo + so[q]] = o1;
+            }
+        }
+        __syncthreads();   // buffer `buf` is free for the pass after next
+    }
 }
 
+// out[c][i] = in[c][perm[i]]: with perm = sorted -> caller it brings a block of caller-ordered columns
+// into the operator's sorted point order ahead of the (coalesced) sorted-order kernels, with the
+// inverse permutation it takes results back.  Writes are coalesced; the source column (8 n bytes)
+// stays in L2 while it is gathered from.
+__global__ void __launch_bounds__(256) permute_cols_kernel(const double* __restrict__ in, long ld,
+                                                           const int* __restrict__ perm, long n,
+                                                           double* __restrict__ out, long ldo) {
+    const int c = blockIdx.y;
+    const long base = (long)blockIdx.x * 2048 + threadIdx.x;
+    int idx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) idx[k] = (base + 256 * k < n) ? perm[base + 256 * k] : 0;
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = in[(long)c * ld + idx[k]];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (base + 256 * k < n) out[(long)c * ldo + base + 256 * k] = v[k];
+}
+
+int permute_cols(const PointSet& ps, bool to_sorted, const double* in, long ld, int ncols, double* out,
+                 long ldo, cudaStream_t st) {
+    if (ncols == 0) return 0;
+    ProfScope prof(PROF_OTHER, st);
+    dim3 grid((unsigned)ceil_div(ps.n, 2048), (unsigned)ncols);
+    permute_cols_kernel<<<grid, 256, 0, st>>>(in, ld, to_sorted ? ps.perm : ps.iperm, ps.n, out, ldo);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
 static InterpArgs make_args(const PointSet& ps, const ColumnView& cv) {
     InterpArgs a = {};
     a.u0 = ps.u[0]; a.u1 = ps.u[1];
     a.i00 = ps.i0[0]; a.i01 = ps.i0[1];
-    a.perm = ps.perm;
+    a.perm_in = (cv.sorted_in || ps.identity) ? nullptr : ps.perm;
+    a.perm_out = (cv.sorted_out || ps.identity) ? nullptr : ps.perm;
     a.bin_start = ps.bin_start;
     a.out_start = ps.out_start_dev;
-    a.in = cv.in; a.out = cv.out; a.ld = cv.ld; a.ncols = cv.ncols;
+    a.in = cv.in; a.out = cv.out; a.ld = cv.ld; a.ldo = cv.ld_out ? cv.ld_out : cv.ld;
+    a.ncols = cv.ncols;
     a.in_scale = cv.in_scale; a.active = cv.active;
     a.grid_pitch = ps.grid_pitch;
     a.D = ps.D; a.m0 = ps.m[0]; a.m1 = ps.m[1];
-    a.NB = ps.NB; a.nb1 = ps.nb[1];
+    a.NB = ps.NB; a.nb0 = ps.nb[0]; a.nb1 = ps.nb[1];
     return a;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    LMC_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) {
@@ -778,51 +945,41 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     InterpArgs a = make_args(ps, cv);
     a.G = G;
     ProfScope prof(PROF_TO_GRID, st);
-    const bool perm = !(cv.sorted_io || ps.identity);
+    const int npairs = (cv.ncols + 1) / 2;
     if (ps.ndim == 1) {
-        const int threads = 256, PT = 4;
-        const int ltpb = threads_per_bin_log2(ps);
-        const int TC = (threads >> ltpb) - 3;
-        a.tiles = ceil_div(ps.m[0], TC);
-        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(cv.ncols, PT));
-        if (perm) to_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a, ltpb);
-        else to_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a, ltpb);
-    } else {
-        a.tiles1 = ceil_div(ps.m[1], kTY);
-        a.tiles = ceil_div(ps.m[0], kTX) * a.tiles1;
-        const int npairs = (cv.ncols + 1) / 2;
-        if (ps.max_tile_pts <= kCap2) {
-            static bool attr2 = false;
-            if (!attr2) {
-                LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_v2_kernel<true>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)));
-                LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_v2_kernel<false>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tile2Smem)));
-                attr2 = true;
-            }
-            // enough CTAs to fill the machine a few times over, as many pairs per CTA as that allows
-            const long ctas1 = (long)a.tiles * ps.D;
-            int ppc = (int)std::max<long>(1, std::min<long>(8, (ctas1 * npairs) / (148L * 3 * 4)));
-            ppc = std::min(ppc, npairs);
-            dim3 grid2((unsigned)ctas1, (unsigned)ceil_div(npairs, ppc));
-            if (perm) to_grid_2d_v2_kernel<true><<<grid2, 256, sizeof(Tile2Smem), st>>>(a, ppc);
-            else to_grid_2d_v2_kernel<false><<<grid2, 256, sizeof(Tile2Smem), st>>>(a, ppc);
-            count_launch();
-            LMC_CHECK(cudaGetLastError());
-            return 0;
-        }
-        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)npairs);
-        const size_t smem = sizeof(double) * 32 * kBX * kBY;
+        constexpr int G1 = 8, CAP1 = 512;
+        typedef Scatter1Smem<G1, CAP1> Smem;
         static bool attr = false;
-        if (!attr) {
-            LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_kernel<true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LMC_CHECK(cudaFuncSetAttribute(to_grid_2d_kernel<false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
+        if (!attr) { LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1>, sizeof(Smem))); attr = true; }
+        const int TC = 256 / G1 - 3;
+        a.tiles = ceil_div(ps.m[0], TC);
+        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
+        to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
+    } else {
+        static const int variant = env_int("LMC_TOGRID2D", 3);
+        constexpr int G = 16, TX = 8, TY = 8, CAP = 304;
+        if (variant >= 3 && ps.max_tile_pts_8x8 <= CAP) {
+            typedef Tile3Smem<G, TX, TY, CAP> Smem;
+            static bool attr3 = false;
+            if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }
+            a.tiles1 = ceil_div(ps.m[1], TY);
+            a.tiles = ceil_div(ps.m[0], TX) * a.tiles1;
+            const int ngroups = ceil_div(npairs, G);
+            const long ctas1 = (long)a.tiles * ps.D;
+            // all groups in one CTA (weights computed once) unless that leaves the machine underfilled
+            int gpc = ngroups;
+            while (gpc > 1 && ctas1 * ceil_div(ngroups, gpc) < 148L * 2 * 4) gpc = (gpc + 1) / 2;
+            dim3 grid3((unsigned)ctas1, (unsigned)ceil_div(ngroups, gpc));
+            to_grid_2d_v3_kernel<G, TX, TY, CAP><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
+        } else {
+            a.tiles1 = ceil_div(ps.m[1], kTY);
+            a.tiles = ceil_div(ps.m[0], kTX) * a.tiles1;
+            dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)npairs);
+            const size_t smem = sizeof(double) * 32 * kBX * kBY;
+            static bool attr = false;
+            if (!attr) { LMC_TRY(set_smem(to_grid_2d_kernel, smem)); attr = true; }
+            to_grid_2d_kernel<<<grid, 384, smem, st>>>(a);
         }
-        if (perm) to_grid_2d_kernel<true><<<grid, 384, smem, st>>>(a);
-        else to_grid_2d_kernel<false><<<grid, 384, smem, st>>>(a);
     }
     count_launch();
     LMC_CHECK(cudaGetLastError());
@@ -836,25 +993,38 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
     a.Gc = G;
     ProfScope prof(PROF_FROM_GRID, st);
     a.noise = noise;
-    const bool perm = !(cv.sorted_io || ps.identity);
+    long maxlen = 0;
+    for (int d = 0; d < ps.D; ++d) maxlen = std::max(maxlen, ps.out_start[d + 1] - ps.out_start[d]);
+    if (maxlen == 0) return 0;
+    const int npairs = (cv.ncols + 1) / 2;
     if (ps.ndim == 1) {
-        const int threads = 256, PT = 4;
-        const int ltpb = threads_per_bin_log2(ps);
-        a.tiles = ceil_div(ps.m[0] + 3, threads >> ltpb);
-        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(cv.ncols, PT));
-        if (perm) from_grid_1d_kernel<4, true><<<grid, threads, 0, st>>>(a, ltpb);
-        else from_grid_1d_kernel<4, false><<<grid, threads, 0, st>>>(a, ltpb);
+        const long ctas1 = (long)ceil_div(maxlen, 256) * ps.D;
+        int ppc = npairs;   // all pairs per thread (weights once) unless that underfills the machine
+        while (ppc > 1 && ctas1 * ceil_div(npairs, ppc) < 148L * 8) ppc = (ppc + 1) / 2;
+        dim3 grid((unsigned)ceil_div(maxlen, 256), (unsigned)ps.D, (unsigned)ceil_div(npairs, ppc));
+        from_grid_1d_v3_kernel<<<grid, 256, 0, st>>>(a, ppc);
     } else {
-        long maxlen = 0;
-        for (int d = 0; d < ps.D; ++d) maxlen = std::max(maxlen, ps.out_start[d + 1] - ps.out_start[d]);
-        if (maxlen == 0) return 0;
-        const int npairs = (cv.ncols + 1) / 2;
-        const long ctas1 = (long)ceil_div(maxlen, 128) * ps.D;
-        int ppc = (int)std::max<long>(1, std::min<long>(8, (ctas1 * npairs) / (148L * 16 * 4)));
-        ppc = std::min(ppc, npairs);
-        dim3 grid((unsigned)ceil_div(maxlen, 128), (unsigned)ps.D, (unsigned)ceil_div(npairs, ppc));
-        if (perm) from_grid_2d_v2_kernel<true><<<grid, 128, 0, st>>>(a, ppc);
-        else from_grid_2d_v2_kernel<false><<<grid, 128, 0, st>>>(a, ppc);
+        static const int variant = env_int("LMC_FROMGRID2D", 3);
+        constexpr int GP = 8, TB = 16;
+        if (variant >= 3 && ps.max_gather_tile_pts <= 512) {
+            typedef Gather3Smem<GP, TB> Smem;
+            static bool attr = false;
+            if (!attr) { LMC_TRY(set_smem(from_grid_2d_v3_kernel<GP, TB>, sizeof(Smem))); attr = true; }
+            a.tiles1 = ceil_div(ps.nb[1], TB);
+            a.tiles = ceil_div(ps.nb[0], TB) * a.tiles1;
+            const long ctas1 = (long)a.tiles * ps.D;
+            const int npass = ceil_div(npairs, GP);
+            int ppc = npass;
+            while (ppc > 1 && ctas1 * ceil_div(npass, ppc) < 148L * 2 * 4) ppc = (ppc + 1) / 2;
+            dim3 grid((unsigned)ctas1, (unsigned)ceil_div(npass, ppc));
+            from_grid_2d_v3_kernel<GP, TB><<<grid, 256, sizeof(Smem), st>>>(a, ppc);
+        } else {
+            const long ctas1 = (long)ceil_div(maxlen, 128) * ps.D;
+            int ppc = (int)std::max<long>(1, std::min<long>(8, (ctas1 * npairs) / (148L * 16 * 4)));
+            ppc = std::min(ppc, npairs);
+            dim3 grid((unsigned)ceil_div(maxlen, 128), (unsigned)ps.D, (unsigned)ceil_div(npairs, ppc));
+            from_grid_2d_v2_kernel<<<grid, 128, 0, st>>>(a, ppc);
+        }
     }
     count_launch();
     LMC_CHECK(cudaGetLastError());

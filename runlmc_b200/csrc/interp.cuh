@@ -14,8 +14,10 @@ struct PointSet {
     long NB = 0;          // bins per output
     long grid_pitch = 0;  // cells allocated per (pair, output) slab
     bool identity = false;  // sorted order == caller's order
-    int max_tile_pts = 0;   // 2-D: largest point count of a 16x16-cell tile incl. its 3-bin halo
+    int max_tile_pts_8x8 = 0;     // 2-D: most points in the 11x11 bins around an 8x8-cell scatter tile
+    int max_gather_tile_pts = 0;  // 2-D: most points in a 16x16-bin gather tile
     int* perm = nullptr;     // [n] sorted position -> caller's index
+    int* iperm = nullptr;    // [n] caller's index -> sorted position (nullptr when identity)
     double* u[2] = {nullptr, nullptr};  // [n] fractional offsets (sorted order)
     int* i0[2] = {nullptr, nullptr};    // [n] clamped base index (sorted order)
     int* bin_start = nullptr;           // [D*NB + 1] offsets into the sorted arrays
@@ -30,15 +32,21 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
 void free_points(PointSet* ps);
 
 struct ColumnView {
-    const double* in = nullptr;  // [ncols][ld] input vectors (caller's order unless sorted_io)
-    double* out = nullptr;       // [ncols][ld] outputs
+    const double* in = nullptr;  // [ncols][ld] input vectors (caller's order unless sorted_in)
+    double* out = nullptr;       // [ncols][ld_out] outputs (caller's order unless sorted_out)
     long ld = 0;
+    long ld_out = 0;             // 0: same as ld
     int ncols = 0;
     const double* in_scale = nullptr;  // optional per-column factor applied to `in`
     const int* active = nullptr;       // optional per-column flag; pairs with no active column are skipped
-    bool sorted_io = false;            // vectors already in the operator's sorted order
+    bool sorted_in = false;            // `in` already is in the operator's sorted point order
+    bool sorted_out = false;           // `out` is wanted in sorted order
 };
 
+// block of columns between the caller's point order and the sorted order (out[c][i] = in[c][p[i]],
+// p = perm when to_sorted, else its inverse)
+int permute_cols(const PointSet& ps, bool to_sorted, const double* in, long ld, int ncols, double* out,
+                 long ldo, cudaStream_t st);
 // G[pair][d][cell] (complex pairs of columns 2p, 2p+1)  <-  W^T in     (deterministic, no atomics)
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st);
 // out = W G (+ noise_d * in when noise != nullptr)

@@ -331,7 +331,7 @@ struct FusedOperator : MinresOperator {
     int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
               cudaStream_t st) override {
         ColumnView cv;
-        cv.in = in; cv.out = out; cv.ld = n; cv.ncols = P; cv.sorted_io = true;
+        cv.in = in; cv.out = out; cv.ld = n; cv.ncols = P; cv.sorted_in = cv.sorted_out = true;
         cv.in_scale = in_scale; cv.active = active;
         return op_mvm(op, cv, st);
     }

@@ -86,18 +86,40 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
     LMC_TRY(op_ensure_workspace(op));
     const int npairs = (cv.ncols + 1) / 2;
+    const long n = op->ps.n;
+    // Large blocks in the caller's point order are first brought into sorted order (one L2-friendly
+    // gather per column), run through the coalesced sorted-order kernels in place, and taken back
+    // with the inverse permutation.  Small blocks skip the two extra launches and let the kernels
+    // index through the permutation.
+    const bool big = !op->ps.identity && n * (long)cv.ncols >= (1L << 20);
+    const bool presort = big && !cv.sorted_in, postsort = presort && !cv.sorted_out;
+    if (presort && !op->Vs) LMC_CHECK(cudaMalloc(&op->Vs, sizeof(double) * (size_t)2 * op->g_pairs * n));
+    const long ldo = cv.ld_out ? cv.ld_out : cv.ld;
     for (int p0 = 0; p0 < npairs; p0 += op->g_pairs) {
         const int cnt = std::min(op->g_pairs, npairs - p0);
         ColumnView t = cv;
         const int c0 = 2 * p0;
         t.in = cv.in + (long)c0 * cv.ld;
-        t.out = cv.out + (long)c0 * cv.ld;
+        t.out = cv.out + (long)c0 * ldo;
+        t.ld_out = ldo;
         t.ncols = std::min(2 * cnt, cv.ncols - c0);
         t.in_scale = cv.in_scale ? cv.in_scale + c0 : nullptr;
         t.active = cv.active ? cv.active + c0 : nullptr;
+        if (presort) {
+            LMC_TRY(permute_cols(op->ps, true, t.in, cv.ld, t.ncols, op->Vs, n, st));
+            t.in = op->Vs;
+            t.ld = n;
+            t.sorted_in = true;
+        }
+        if (postsort) {   // the gather kernel reads in[c][i] and writes out[c][i] from the same thread
+            t.out = op->Vs;
+            t.ld_out = n;
+            t.sorted_out = true;
+        }
         LMC_TRY(to_grid(op->ps, t, op->G, st));
         LMC_TRY(op_grid_block(op, op->G, cnt, st));
         LMC_TRY(from_grid(op->ps, t, op->G, op->noise, st));
+        if (postsort) LMC_TRY(permute_cols(op->ps, false, op->Vs, n, t.ncols, cv.out + (long)c0 * ldo, ldo, st));
     }
     return 0;
 }
@@ -121,6 +143,7 @@ lmc_op::~lmc_op() {
     cudaFree(noise);
     cudaFree(G);
     cudaFree(S);
+    cudaFree(Vs);
 }
 
 lmc_bttb::~lmc_bttb() {

@@ -29,6 +29,7 @@ struct lmc_op {
     // grid-stage workspace for `tile_pairs` RHS pairs
     cplx* G = nullptr;        // [g_pairs][D][grid_pitch]  grid-side vectors of a block of RHS pairs
     cplx* S = nullptr;        // [tile_pairs][D][bins]     spectra of one L2-sized sub-tile of pairs
+    double* Vs = nullptr;     // [2 g_pairs][n] sorted-order copy of a block of caller-ordered columns
     int g_pairs = 0;
     int tile_pairs = 0;
     // host-buffer entry points: double-buffered device staging + 3 streams (copy in / compute / copy out)

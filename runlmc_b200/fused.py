@@ -139,6 +139,17 @@ class FusedLMC:
                                    _dev(out), nat.current_stream_ptr()))
         return out
 
+    def mvm_sorted_device(self, V, out=None):
+        """Same as mvm_device with V and the result in the operator's sorted point order
+        (column i is the caller's point perm()[i]) -- the solver's native layout."""
+        torch = nat.require_cuda()
+        assert V.is_cuda and V.dtype == torch.float64 and V.is_contiguous()
+        if out is None:
+            out = torch.empty_like(V)
+        nat.check(nat.lib.lmc_mvm_sorted(self._h, _dev(V), V.shape[1], V.shape[0],
+                                          _dev(out), nat.current_stream_ptr()))
+        return out
+
     def to_grid_device(self, V):
         torch = nat.require_cuda()
         G = torch.empty((V.shape[0], self.D * self.m), dtype=torch.float64, device=V.device)

@@ -80,6 +80,12 @@ def test_stages_and_mvm(name):
     for p in (1, 2, 4):
         out = op.mvm_device(Vd[:p].contiguous()).cpu().numpy()
         assert rel_err(out, want[:p]) < MVM_TOL
+    # the solver's layout: vectors in the operator's sorted point order
+    perm = op.perm()
+    assert sorted(perm.tolist()) == list(range(prob.n))
+    Vs = torch.as_tensor(np.ascontiguousarray(V[:, perm]), device='cuda')
+    out = op.mvm_sorted_device(Vs).cpu().numpy()
+    assert rel_err(out, want[:, perm]) < MVM_TOL
 
 
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
