@@ -250,15 +250,28 @@ static inline StageTw stage_tw_layout(int L, const FftPlan& pl) {
     return t;
 }
 
-template <int R, bool INV, bool HIN, bool HOUT, bool GLOBAL_IO>
+// LSPAN >= 0: log2 of the butterfly span is a compile-time constant, which turns every padded
+// shared-memory index into `pad_idx(base) + constant` and every twiddle index into `o + constant`
+// (about 10 integer instructions per radix-8 butterfly instead of ~100).  LSPAN < 0: run-time span.
+template <int R, int LSPAN, bool INV, bool HIN, bool HOUT, bool GLOBAL_IO>
 __device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx* tws,
                                            const cplx* __restrict__ gsrc, cplx* gdst, int valid) {
-    const int span = Ns / R;
+    constexpr int lR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+    const int lspan = LSPAN >= 0 ? LSPAN : (31 - __clz(Ns)) - lR;   // powers of two: shifts only
+    const int span = 1 << lspan;
+    const int lNs = lspan + lR;
+    // padded distance between the R elements of a butterfly: exact because base + r*span never
+    // carries across a multiple of 8 differently from base (span % 8 == 0, or span == 1 with
+    // base % 8 == 0 and R <= 8); spans 2 and 4 only occur for L < 64 and take the general form
+    const bool lin = span >= 8 || (span == 1 && R == 8);
+    const int pstep = span >= 8 ? span + (span >> 3) : 1;
+    const int nb = L >> lR;
     const int lane = threadIdx.x & 31;
-    for (int b = lane; b < L / R; b += 32) {
-        const int blk = b / span;
-        const int o = b - blk * span;
-        const int base = blk * Ns + o;
+    for (int b = lane; b < nb; b += 32) {
+        const int blk = b >> lspan;
+        const int o = b & (span - 1);
+        const int base = (blk << lNs) + o;
+        const int pbase = pad_idx(base);
         cplx x[R];
         if (!INV) {
 #pragma unroll
@@ -266,7 +279,7 @@ __device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx
                 if (HIN && r >= R / 2) continue;
                 const int e = base + r * span;
                 if (GLOBAL_IO) x[r] = (e < valid) ? gsrc[e] : make_double2(0.0, 0.0);
-                else x[r] = line[pad_idx(e)];
+                else x[r] = line[lin ? pbase + r * pstep : pad_idx(e)];
             }
             Dft<R, false, HIN, false>::run(x);
             if (span > 1) {
@@ -274,10 +287,10 @@ __device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx
                 for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tws[(q - 1) * span + o]);
             }
 #pragma unroll
-            for (int q = 0; q < R; ++q) line[pad_idx(base + q * span)] = x[q];
+            for (int q = 0; q < R; ++q) line[lin ? pbase + q * pstep : pad_idx(base + q * span)] = x[q];
         } else {
 #pragma unroll
-            for (int q = 0; q < R; ++q) x[q] = line[pad_idx(base + q * span)];
+            for (int q = 0; q < R; ++q) x[q] = line[lin ? pbase + q * pstep : pad_idx(base + q * span)];
             if (span > 1) {
 #pragma unroll
                 for (int q = 1; q < R; ++q) x[q] = cmulc(x[q], tws[(q - 1) * span + o]);
@@ -288,7 +301,7 @@ __device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx
                 if (HOUT && r >= R / 2) continue;
                 const int e = base + r * span;
                 if (GLOBAL_IO) { if (e < valid) gdst[e] = x[r]; }
-                else line[pad_idx(e)] = x[r];
+                else line[lin ? pbase + r * pstep : pad_idx(e)] = x[r];
             }
         }
     }
@@ -297,9 +310,19 @@ __device__ __forceinline__ void warp_stage(cplx* line, int L, int Ns, const cplx
 template <bool INV, bool HALF, bool GLOBAL_IO>
 __device__ __forceinline__ void warp_stage_dispatch(int R, cplx* line, int L, int Ns, const cplx* tws,
                                                     const cplx* gsrc, cplx* gdst, int valid) {
-    if (R == 8) warp_stage<8, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
-    else if (R == 4) warp_stage<4, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
-    else warp_stage<2, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+    if (R == 8) {
+        // the spans a radix-8 stage can have in a plan (2|4)? 8 8 ... 8 are 8^k, k = 0..3
+        switch (Ns) {
+            case 8: warp_stage<8, 0, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid); break;
+            case 64: warp_stage<8, 3, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid); break;
+            case 512: warp_stage<8, 6, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid); break;
+            default: warp_stage<8, 9, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid); break;
+        }
+    } else if (R == 4) {
+        warp_stage<4, -1, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+    } else {
+        warp_stage<2, -1, INV, !INV && HALF, INV && HALF, GLOBAL_IO>(line, L, Ns, tws, gsrc, gdst, valid);
+    }
 }
 
 // forward transform of one line by the calling warp: global (valid prefix, rest zero) -> shared

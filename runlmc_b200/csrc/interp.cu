@@ -502,6 +502,7 @@ struct Tile3Smem {
     double wy[4][CAP];
     double v[2][CAP * (G + 1)];   // [re | im][point][pair]
     int src[CAP];
+    unsigned char by[CAP];        // bin column of the point inside the window
     int bin[BX][BY + 1];          // local offset of every bin of the window (+ end of row)
     int row_beg[BX];
     int row_off[BX + 1];
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
 #pragma unroll
         for (int k = 0; k < 4; ++k) { s.wx[k][i] = wx[k]; s.wy[k][i] = wy[k]; }
         s.src[i] = a.perm_in ? a.perm_in[gidx] : gidx;
+        s.by[i] = (unsigned char)(a.i01[gidx] + 2 - cy0);
     }
     __syncthreads();
 
@@ -602,24 +604,22 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
 #pragma unroll
                 for (int aa = 0; aa < 7; ++aa) {
                     // bin row 4 sx + aa: cell c of the strip takes x tap c - aa + 3 from it
+                    // the 4 bins (row, sy .. sy + 3) are one contiguous run of points; the point in bin
+                    // column by feeds cell jy with y tap 3 - (by - sy)
                     const int* brow = &s.bin[4 * sx + aa][sy];
-                    int i = brow[0];
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {   // bin (row, sy + b) feeds cell jy with y tap 3 - b
-                        const int iend = brow[b + 1];
-                        const double* wyp = s.wy[3 - b];
+                    const int iend = brow[4];
+                    const double* wyb = &s.wy[0][0] + (3 + sy) * CAP;
 #pragma unroll 1
-                        for (; i < iend; ++i) {
-                            const double wyv = wyp[i];
-                            const double t0 = wyv * vre[i * VP], t1 = wyv * vim[i * VP];
+                    for (int i = brow[0]; i < iend; ++i) {
+                        const double wyv = wyb[i - (int)s.by[i] * CAP];
+                        const double t0 = wyv * vre[i * VP], t1 = wyv * vim[i * VP];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const int kx = c - aa + 3;
-                                if (kx >= 0 && kx <= 3) {
-                                    const double wxv = s.wx[kx][i];
-                                    acc[c][0] = fma(wxv, t0, acc[c][0]);
-                                    acc[c][1] = fma(wxv, t1, acc[c][1]);
-                                }
+                        for (int c = 0; c < 4; ++c) {
+                            const int kx = c - aa + 3;
+                            if (kx >= 0 && kx <= 3) {
+                                const double wxv = s.wx[kx][i];
+                                acc[c][0] = fma(wxv, t0, acc[c][0]);
+                                acc[c][1] = fma(wxv, t1, acc[c][1]);
                             }
                         }
                     }
@@ -831,6 +831,25 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
     }
     const double nz = a.noise ? a.noise[d] : 0.0;
 
+    // noise term inputs in[c][i] of the two columns of a pair, fetched one pair ahead of their use so
+    // the global-load latency hides behind the 16-tap arithmetic of the current pair
+    auto fetch_in = [&](int pair, double (&v)[2][2]) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) v[q][0] = v[q][1] = 0.0;
+        if (!a.noise || pair >= pair_hi) return;
+        const int cA = 2 * pair, cB = cA + 1;
+        const bool actA = !a.active || a.active[cA];
+        const bool actB = cB < a.ncols && (!a.active || a.active[cB]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!have[q]) continue;
+            if (actA) v[q][0] = a.in[(long)cA * a.ld + si[q]];
+            if (actB) v[q][1] = a.in[(long)cB * a.ld + si[q]];
+        }
+    };
+    double cur[2][2], nxt[2][2];
+    fetch_in(pair_lo, cur);
+
     int buf = 0;
     for (int pbase = pair_lo; pbase < pair_hi; pbase += GP, buf ^= 1) {
         if (pbase + GP < pair_hi) { stage(pbase + GP, buf ^ 1); cp_async_wait_1(); }
@@ -840,39 +859,41 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
         for (int p = 0; p < GP; ++p) {
             const int pair = pbase + p;
             if (pair >= pair_hi) break;
+            fetch_in(pair + 1, nxt);
             const int cA = 2 * pair, cB = cA + 1;
             const bool hasB = cB < a.ncols;
             const bool actA = !a.active || a.active[cA];
             const bool actB = hasB && (!a.active || a.active[cB]);
-            if (!actA && !actB) continue;
-            const cplx* cl = s.cell[buf][p];
-            const double scA = a.in_scale ? a.in_scale[cA] : 1.0;
-            const double scB = (a.in_scale && hasB) ? a.in_scale[cB] : 1.0;
+            if (actA || actB) {
+                const cplx* cl = s.cell[buf][p];
+                const double scA = a.in_scale ? a.in_scale[cA] : 1.0;
+                const double scB = (a.in_scale && hasB) ? a.in_scale[cB] : 1.0;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (!have[q]) continue;
-                double inA = 0.0, inB = 0.0;
-                if (a.noise) {
-                    if (actA) inA = a.in[(long)cA * a.ld + si[q]] * scA;
-                    if (actB) inB = a.in[(long)cB * a.ld + si[q]] * scB;
-                }
-                double o0 = 0.0, o1 = 0.0;
+                for (int q = 0; q < 2; ++q) {
+                    if (!have[q]) continue;
+                    double o0 = 0.0, o1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    double r0 = 0.0, r1 = 0.0;
+                    for (int k = 0; k < 4; ++k) {
+                        double r0 = 0.0, r1 = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const cplx v = cl[off[q][k] + oy[q][j]];
-                        r0 = fma(wy[q][j], v.x, r0);
-                        r1 = fma(wy[q][j], v.y, r1);
+                        for (int j = 0; j < 4; ++j) {
+                            const cplx v = cl[off[q][k] + oy[q][j]];
+                            r0 = fma(wy[q][j], v.x, r0);
+                            r1 = fma(wy[q][j], v.y, r1);
+                        }
+                        o0 = fma(wx[q][k], r0, o0);
+                        o1 = fma(wx[q][k], r1, o1);
                     }
-                    o0 = fma(wx[q][k], r0, o0);
-                    o1 = fma(wx[q][k], r1, o1);
+                    if (a.noise) {
+                        o0 = fma(nz, cur[q][0] * scA, o0);
+                        o1 = fma(nz, cur[q][1] * scB, o1);
+                    }
+                    if (actA) a.out[(long)cA * a.ldo + so[q]] = o0;
+                    if (actB) a.out[(long)cB * a.ldo + so[q]] = o1;
                 }
-                if (a.noise) { o0 = fma(nz, inA, o0); o1 = fma(nz, inB, o1); }
-                if (actA) a.out[(long)cA * a.ldo + so[q]] = o0;
-                if (actB) a.out[(long)cB * a.ldo + so[q]] = o1;
             }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { cur[q][0] = nxt[q][0]; cur[q][1] = nxt[q][1]; }
         }
         __syncthreads();   // buffer `buf` is free for the pass after next
     }

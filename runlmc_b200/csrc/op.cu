@@ -8,6 +8,7 @@
 #include "op.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace lmc {
@@ -36,12 +37,15 @@ void prof_end(int cat, cudaStream_t st) {
     g_prof_recs.push_back({cat, g_prof_open[cat], e});
 }
 
-static const size_t kSpectrumTileBytes = 96ull << 20;  // keep the FFT working set near L2 size
+static size_t spectrum_tile_bytes() {   // pairs per spectral launch: large launches beat L2 residency (measured)
+    static const char* e = getenv("LMC_SPECTRUM_TILE_MB");
+    return (e ? (size_t)atoi(e) : 1024) << 20;
+}
 
 int op_ensure_workspace(lmc_op* op) {
     if (op->G) return 0;
     const size_t per_pair = sizeof(cplx) * (size_t)op->D * op->emb.bins;
-    int tile = (int)std::max<size_t>(1, kSpectrumTileBytes / per_pair);
+    int tile = (int)std::max<size_t>(1, spectrum_tile_bytes() / per_pair);
     tile = std::min(tile, 256);
     op->tile_pairs = tile;
     const size_t fpp = sizeof(cplx) * op->eng.fused_elems_per_pair(op->D);
@@ -49,7 +53,7 @@ int op_ensure_workspace(lmc_op* op) {
     // interpolation runs over a wider block of pairs than the spectral stage: the grid slabs are
     // small (cells << bins) and the scatter/gather kernels amortise their per-point weights over pairs
     const size_t per_pair_g = sizeof(cplx) * (size_t)op->D * op->emb.grid_pitch;
-    int gp = (int)std::max<size_t>(tile, std::min<size_t>(64, (1ull << 30) / per_pair_g));
+    int gp = (int)std::max<size_t>(tile, std::min<size_t>(128, (3ull << 29) / per_pair_g));
     op->g_pairs = gp;
     const size_t gbytes = per_pair_g * gp;
     LMC_CHECK(cudaMalloc(&op->G, gbytes));
@@ -95,8 +99,11 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
     const bool presort = big && !cv.sorted_in, postsort = presort && !cv.sorted_out;
     if (presort && !op->Vs) LMC_CHECK(cudaMalloc(&op->Vs, sizeof(double) * (size_t)2 * op->g_pairs * n));
     const long ldo = cv.ld_out ? cv.ld_out : cv.ld;
-    for (int p0 = 0; p0 < npairs; p0 += op->g_pairs) {
-        const int cnt = std::min(op->g_pairs, npairs - p0);
+    // equal blocks of pairs (a 129-column block is one block of 65 pairs or 33 + 32, never 64 + 1)
+    const int nblocks = ceil_div(npairs, op->g_pairs);
+    const int per_block = ceil_div(npairs, nblocks);
+    for (int p0 = 0; p0 < npairs; p0 += per_block) {
+        const int cnt = std::min(per_block, npairs - p0);
         ColumnView t = cv;
         const int c0 = 2 * p0;
         t.in = cv.in + (long)c0 * cv.ld;

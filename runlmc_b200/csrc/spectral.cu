@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(256) fft_rows_T_kernel(const RowsTArgs a) {
 template <int D>
 struct MixB {
     double b[8][D][D];
-    __device__ __forceinline__ void apply(const double* f, int Q, const cplx* x, cplx* y) const {
+    // in place on the D values of one bin
+    __device__ __forceinline__ void apply(const double* f, int Q, cplx* x) const {
+        cplx y[D];
 #pragma unroll
         for (int dp = 0; dp < D; ++dp) {
             double m[D];
@@ -483,6 +485,8 @@ struct MixB {
             }
             y[dp] = make_double2(yr, yi);
         }
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = y[d];
     }
 };
 
@@ -492,39 +496,46 @@ struct MixLR {
     double a[8][kMaxRankPerKernel][D];
     double kappa[8][D];
     int rank[8];
-    __device__ __forceinline__ void apply(const double* f, int Q, const cplx* x, cplx* y) const {
+    // In place.  The mix is a real matrix, so the real and the imaginary parts of the bin are two
+    // independent real products: they are done one after the other with one set of D accumulators,
+    // which keeps the live registers at ~3D doubles (x complex + y) instead of 5D.
+    __device__ __forceinline__ void apply(const double* f, int Q, cplx* x) const {
         double ks[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { ks[d] = 0.0; y[d] = make_double2(0.0, 0.0); }
+        for (int d = 0; d < D; ++d) ks[d] = 0.0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (q < Q) {   // warp-uniform
-#pragma unroll
-                for (int r = 0; r < kMaxRankPerKernel; ++r) {
-                    if (r < rank[q]) {   // warp-uniform
-                        double tr = 0.0, ti = 0.0;
-#pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            tr = fma(a[q][r][d], x[d].x, tr);
-                            ti = fma(a[q][r][d], x[d].y, ti);
-                        }
-                        tr *= f[q];
-                        ti *= f[q];
-#pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            y[d].x = fma(a[q][r][d], tr, y[d].x);
-                            y[d].y = fma(a[q][r][d], ti, y[d].y);
-                        }
-                    }
-                }
 #pragma unroll
                 for (int d = 0; d < D; ++d) ks[d] = fma(f[q], kappa[q][d], ks[d]);
             }
         }
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            y[d].x = fma(ks[d], x[d].x, y[d].x);
-            y[d].y = fma(ks[d], x[d].y, y[d].y);
+        for (int part = 0; part < 2; ++part) {
+            double y[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < Q) {   // warp-uniform
+#pragma unroll
+                    for (int r = 0; r < kMaxRankPerKernel; ++r) {
+                        if (r < rank[q]) {   // warp-uniform
+                            double t = 0.0;
+#pragma unroll
+                            for (int d = 0; d < D; ++d) t = fma(a[q][r][d], part ? x[d].y : x[d].x, t);
+                            t *= f[q];
+#pragma unroll
+                            for (int d = 0; d < D; ++d) y[d] = fma(a[q][r][d], t, y[d]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (part) x[d].y = fma(ks[d], x[d].y, y[d]);
+                else x[d].x = fma(ks[d], x[d].x, y[d]);
+            }
         }
     }
 };
@@ -575,10 +586,9 @@ __global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, 
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             f[q] = (q < a.Q) ? __ldg(&a.specL[((long)q * a.n_lines + line0 + ll) * L + p]) : 0.0;
-        cplx y[D];
-        mb.apply(f, a.Q, x, y);
+        mb.apply(f, a.Q, x);
 #pragma unroll
-        for (int d = 0; d < D; ++d) col[d * pitch] = y[d];
+        for (int d = 0; d < D; ++d) col[d * pitch] = x[d];
     }
     __syncthreads();
     for (int li = warp; li < nl; li += nwarps) {
