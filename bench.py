@@ -169,22 +169,30 @@ class ClockSampler(threading.Thread):
 # roofline bookkeeping (DESIGN.md "Algorithmic bytes")
 # --------------------------------------------------------------------------
 def family_bytes(family, prob, P, bins, gpitch):
-    """Algorithmic HBM bytes of one step for a kernel family."""
+    """Algorithmic HBM bytes of one step for a kernel family: the vectors and
+    coordinates a stage must read/write plus its grid-side slabs once in and once out."""
     n, d, D = prob.n, prob.ndim, prob.D
     pairs = (P + 1) // 2
-    slab = 16.0 * D * pairs
+    slab = 16.0 * D * pairs                     # bytes per complex element over all (pair, output) slabs
     if family == 'to_grid':
         return 8.0 * n * P + 8.0 * d * n + slab * gpitch
     if family == 'from_grid':
         return 16.0 * n * P + 8.0 * d * n + slab * gpitch
+    if d == 2:
+        # fused 2-D path: row transforms G <-> S_T[ky][x] (only the m0 non-zero / kept x columns are
+        # stored), column transform + mix + inverse in place on S_T
+        st = float(bins) / (2 * prob.grid_sizes[0]) * (-(-prob.grid_sizes[0] // 8) * 8)
+        if family in ('fft_fwd_contig', 'fft_inv_contig'):
+            return slab * (gpitch + st)
+        if family == 'mix':
+            return slab * 2 * st
+        return 0.0
     if family in ('fft_fwd_contig', 'fft_inv_contig'):
-        rows = prob.grid_sizes[0] if d == 2 else 1
-        emb_row = bins / (2 * prob.grid_sizes[0]) if d == 2 else bins
-        return slab * (gpitch + rows * emb_row) if d == 2 else slab * (gpitch + bins)
+        return slab * (gpitch + bins)
     if family in ('fft_fwd_strided', 'fft_inv_strided'):
         return slab * 1.5 * bins
     if family == 'mix':
-        return slab * 2 * bins
+        return slab * 2 * (bins if bins > 8192 else gpitch)   # short 1-D lines are transformed in the grid slabs
     return 0.0
 
 
@@ -195,11 +203,15 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_traffic(family):
-    """Per-launch DRAM bytes of the family's kernel from the committed ncu summary, if any."""
+def ncu_traffic(workload, family, pairs_per_launch):
+    """Measured DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one launch of the family's
+    kernel: profiles/ncu_traffic.json holds bytes per RHS pair from the committed `ncu --set full`
+    capture of this workload; a launch moves that times the pairs it processes."""
     p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.exists(p):
-        return json.load(open(p)).get(family)
+        per_pair = json.load(open(p)).get(workload, {}).get(family)
+        if per_pair:
+            return per_pair * pairs_per_launch
     return None
 
 
@@ -309,7 +321,8 @@ def run_own(args):
     top = fams[0]
     lpl = max(top['launches_per_step'], 1)
     roofline = {'kernel': top['family'], 'bound': 'hbm', 'achieved': top['alg_gbs'], 'peak': peak, 'unit': 'GB/s',
-                'frac': (top['alg_gbs'] or 0.0) / peak, 'traffic': ncu_traffic(top['family']),
+                'frac': (top['alg_gbs'] or 0.0) / peak,
+                'traffic': ncu_traffic(args.workload, top['family'], ((P + 1) // 2) / lpl),
                 'share_of_step': top['share'], 'alg_bytes_per_launch': top['alg_gb_per_step'] * 1e9 / lpl,
                 'launch_ms': top['ms_per_step'] / lpl, 'peak_source': peak_src}
     b_mvm = 16.0 * prob.n * P + 8.0 * prob.ndim * prob.n + 8.0 * prob.Q * bins + 8.0 * prob.D

@@ -325,6 +325,68 @@ __device__ __forceinline__ void warp_stage_dispatch(int R, cplx* line, int L, in
     }
 }
 
+// First forward stage split in two halves so a kernel can keep the loads of the NEXT line in flight
+// while it transforms the current one: inputs of the (at most NBL) butterflies of a lane in registers.
+// Only the pruned form (inputs >= L/2 are zero) is provided: it is the one every circulant embedding
+// uses.
+template <int R, int NBL>
+struct FirstStageRegs {
+    cplx x[NBL][R / 2];
+};
+
+template <int R, int NBL>
+__device__ __forceinline__ void first_stage_load(FirstStageRegs<R, NBL>& f, const cplx* __restrict__ gsrc,
+                                                 int valid, int L) {
+    constexpr int lR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+    const int span = L >> lR;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < NBL; ++u) {
+        const int b = lane + 32 * u;
+#pragma unroll
+        for (int r = 0; r < R / 2; ++r) {
+            const int e = b + r * span;
+            f.x[u][r] = (b < span && e < valid) ? gsrc[e] : make_double2(0.0, 0.0);
+        }
+    }
+}
+
+template <int R, int NBL>
+__device__ __forceinline__ void first_stage_compute(const FirstStageRegs<R, NBL>& f, cplx* line, int L,
+                                                    const cplx* tws) {
+    constexpr int lR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+    const int span = L >> lR;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < NBL; ++u) {
+        const int b = lane + 32 * u;
+        if (b >= span) continue;
+        cplx x[R];
+#pragma unroll
+        for (int r = 0; r < R / 2; ++r) x[r] = f.x[u][r];
+        Dft<R, false, true, false>::run(x);
+        if (span > 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmul(x[q], tws[(q - 1) * span + b]);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) line[pad_idx(b + q * span)] = x[q];
+    }
+}
+
+// stages 1.. of the forward transform of one line already holding the first stage's output
+__device__ __forceinline__ void warp_fft_forward_rest(cplx* line, int L, const FftPlan& pl, const StageTw& lay,
+                                                      const cplx* tws) {
+    int Ns = L / pl.radix[0];
+    __syncwarp();
+    for (int s = 1; s < pl.nst; ++s) {
+        const int R = pl.radix[s];
+        warp_stage_dispatch<false, false, false>(R, line, L, Ns, tws + lay.off[s], nullptr, nullptr, 0);
+        Ns /= R;
+        __syncwarp();
+    }
+}
+
 // forward transform of one line by the calling warp: global (valid prefix, rest zero) -> shared
 __device__ __forceinline__ void warp_fft_forward(const cplx* gsrc, int valid, cplx* line, int L,
                                                  const FftPlan& pl, const StageTw& lay, const cplx* tws,

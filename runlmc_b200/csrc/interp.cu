@@ -607,17 +607,23 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
                     // the 4 bins (row, sy .. sy + 3) are one contiguous run of points; the point in bin
                     // column by feeds cell jy with y tap 3 - (by - sy)
                     const int* brow = &s.bin[4 * sx + aa][sy];
-                    const int iend = brow[4];
-                    const double* wyb = &s.wy[0][0] + (3 + sy) * CAP;
+                    const int ibeg = brow[0], iend = brow[4];
+                    // running pointers (one add each per point) instead of index arithmetic:
+                    // wx[kx][i] = pw[kx * CAP], wy[3 + sy - by][i] = pwy[-by * CAP], v = pv[0], pv[CAP * VP]
+                    const double* pw = &s.wx[0][0] + ibeg;
+                    const double* pwy = &s.wy[0][0] + (3 + sy) * CAP + ibeg;
+                    const double* pv = vre + ibeg * VP;
+                    const unsigned char* pby = s.by + ibeg;
+                    const unsigned char* pby_end = s.by + iend;
 #pragma unroll 1
-                    for (int i = brow[0]; i < iend; ++i) {
-                        const double wyv = wyb[i - (int)s.by[i] * CAP];
-                        const double t0 = wyv * vre[i * VP], t1 = wyv * vim[i * VP];
+                    for (; pby < pby_end; ++pby, ++pw, ++pwy, pv += VP) {
+                        const double wyv = pwy[-(int)pby[0] * CAP];
+                        const double t0 = wyv * pv[0], t1 = wyv * pv[CAP * VP];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const int kx = c - aa + 3;
                             if (kx >= 0 && kx <= 3) {
-                                const double wxv = s.wx[kx][i];
+                                const double wxv = pw[kx * CAP];
                                 acc[c][0] = fma(wxv, t0, acc[c][0]);
                                 acc[c][1] = fma(wxv, t1, acc[c][1]);
                             }
@@ -790,10 +796,13 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
             if (pair >= pair_hi) break;
             if (!group_active(a, 2 * pair, 2)) continue;
             const cplx* gsl = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
+            // window cell (x, y) holds G[clamp(X0 + x)][clamp(Y0 + y)]: stencils index the window
+            // without clamping and still pick up the edge cell for every clamped tap
+            // (interpolation.py:105-115), so the tap addresses below are compile-time offsets
             for (int c = tid; c < W * W; c += 256) {
                 const int x = c / W, y = c - x * W;
-                const int gx = X0 + x, gy = Y0 + y;
-                if (gx >= 0 && gx < mx && gy >= 0 && gy < my) cp_async16(&s.cell[buf][p][c], gsl + (long)gx * my + gy);
+                const int gx = clampi(X0 + x, 0, mx - 1), gy = clampi(Y0 + y, 0, my - 1);
+                cp_async16(&s.cell[buf][p][c], gsl + (long)gx * my + gy);
             }
         }
         cp_async_commit();
@@ -802,7 +811,7 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
 
     // ---- this thread's (up to) two points ----
     double wx[2][4], wy[2][4];
-    int off[2][4], oy[2][4];
+    int o0[2];       // window offset of the point's first tap
     long si[2], so[2];
     bool have[2];
 #pragma unroll
@@ -817,16 +826,13 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
             keys_weights(a.u0[gi], wx[q]);
             keys_weights(a.u1[gi], wy[q]);
             const int ix0 = a.i00[gi] - 1, iy0 = a.i01[gi] - 1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                off[q][k] = (clampi(ix0 + k, 0, mx - 1) - X0) * W;
-                oy[q][k] = clampi(iy0 + k, 0, my - 1) - Y0;
-            }
+            o0[q] = (ix0 - X0) * W + (iy0 - Y0);
             si[q] = a.perm_in ? (long)a.perm_in[gi] : gi;
             so[q] = a.perm_out ? (long)a.perm_out[gi] : gi;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { wx[q][k] = wy[q][k] = 0.0; off[q][k] = oy[q][k] = 0; }
+            for (int k = 0; k < 4; ++k) wx[q][k] = wy[q][k] = 0.0;
+            o0[q] = 0;
         }
     }
     const double nz = a.noise ? a.noise[d] : 0.0;
@@ -871,25 +877,26 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (!have[q]) continue;
-                    double o0 = 0.0, o1 = 0.0;
+                    const cplx* cq = cl + o0[q];
+                    double r0s = 0.0, r1s = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const cplx v = cl[off[q][k] + oy[q][j]];
+                            const cplx v = cq[k * W + j];
                             r0 = fma(wy[q][j], v.x, r0);
                             r1 = fma(wy[q][j], v.y, r1);
                         }
-                        o0 = fma(wx[q][k], r0, o0);
-                        o1 = fma(wx[q][k], r1, o1);
+                        r0s = fma(wx[q][k], r0, r0s);
+                        r1s = fma(wx[q][k], r1, r1s);
                     }
                     if (a.noise) {
-                        o0 = fma(nz, cur[q][0] * scA, o0);
-                        o1 = fma(nz, cur[q][1] * scB, o1);
+                        r0s = fma(nz, cur[q][0] * scA, r0s);
+                        r1s = fma(nz, cur[q][1] * scB, r1s);
                     }
-                    if (actA) a.out[(long)cA * a.ldo + so[q]] = o0;
-                    if (actB) a.out[(long)cB * a.ldo + so[q]] = o1;
+                    if (actA) a.out[(long)cA * a.ldo + so[q]] = r0s;
+                    if (actB) a.out[(long)cB * a.ldo + so[q]] = r1s;
                 }
             }
 #pragma unroll
@@ -961,11 +968,35 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, bool one_pair_ctas,
+                          cudaStream_t st);
+
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) {
     if (cv.ncols == 0) return 0;
+    ProfScope prof(PROF_TO_GRID, st);
+    const int npairs = (cv.ncols + 1) / 2;
+    // 2-D: a block of 16 k + 1 (or + 2) pairs -- y plus an even number of probes -- would spend a whole
+    // 16-lane group pass of the strip kernel on the odd pair(s); they go through the
+    // one-pair-per-CTA kernel instead.
+    const int rem = npairs % 16;
+    if (ps.ndim == 2 && npairs > 16 && rem >= 1 && rem <= 2) {
+        const int head_pairs = npairs - rem;
+        ColumnView head = cv, tail = cv;
+        head.ncols = 2 * head_pairs;
+        tail.ncols = cv.ncols - 2 * head_pairs;
+        tail.in = cv.in + (long)2 * head_pairs * cv.ld;
+        tail.in_scale = cv.in_scale ? cv.in_scale + 2 * head_pairs : nullptr;
+        tail.active = cv.active ? cv.active + 2 * head_pairs : nullptr;
+        LMC_TRY(to_grid_launch(ps, head, G, false, st));
+        return to_grid_launch(ps, tail, G + (size_t)head_pairs * ps.D * ps.grid_pitch, true, st);
+    }
+    return to_grid_launch(ps, cv, G, false, st);
+}
+
+static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, bool one_pair_ctas,
+                          cudaStream_t st) {
     InterpArgs a = make_args(ps, cv);
     a.G = G;
-    ProfScope prof(PROF_TO_GRID, st);
     const int npairs = (cv.ncols + 1) / 2;
     if (ps.ndim == 1) {
         constexpr int G1 = 8, CAP1 = 512;
@@ -979,7 +1010,7 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     } else {
         static const int variant = env_int("LMC_TOGRID2D", 3);
         constexpr int G = 16, TX = 8, TY = 8, CAP = 304;
-        if (variant >= 3 && ps.max_tile_pts_8x8 <= CAP) {
+        if (variant >= 3 && !one_pair_ctas && ps.max_tile_pts_8x8 <= CAP) {
             typedef Tile3Smem<G, TX, TY, CAP> Smem;
             static bool attr3 = false;
             if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }

@@ -451,151 +451,38 @@ __global__ void __launch_bounds__(256) fft_rows_T_kernel(const RowsTArgs a) {
     }
 }
 
-// Forward transform of the D lines of one RHS pair, per-bin coregionalisation mix, inverse
-// transform -- all in shared memory, in place on global memory.  The mixing matrices travel as
-// kernel parameters so they are constant-bank operands of the DFMAs.
-// Mixing operators, passed as kernel parameters (constant-bank operands).
-// Dense:    y = (sum_q f_q B_q) x                      (Q + 2) D^2 DFMA per bin and RHS pair
-// Low rank: B_q = A_q^T A_q + diag(kappa_q) (the LMC parameterisation, reference
-//           functional_kernel.py:280-287):  y = sum_q f_q A_q^T (A_q x) + (sum_q f_q kappa_q) .* x
-//           sum_q R_q (4D + 2) + (Q + 2) D DFMA
-template <int D>
-struct MixB {
-    double b[8][D][D];
-    // in place on the D values of one bin
-    __device__ __forceinline__ void apply(const double* f, int Q, cplx* x) const {
-        cplx y[D];
-#pragma unroll
-        for (int dp = 0; dp < D; ++dp) {
-            double m[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) m[d] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (q < Q) {   // warp-uniform
-#pragma unroll
-                    for (int d = 0; d < D; ++d) m[d] = fma(f[q], b[q][dp][d], m[d]);
-                }
-            }
-            double yr = 0.0, yi = 0.0;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                yr = fma(m[d], x[d].x, yr);
-                yi = fma(m[d], x[d].y, yi);
-            }
-            y[dp] = make_double2(yr, yi);
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = y[d];
-    }
-};
-
-static const int kMaxRankPerKernel = 2;   // low-rank path: every B_q has rank <= 2 (+ diagonal)
-template <int D>
-struct MixLR {
-    double a[8][kMaxRankPerKernel][D];
-    double kappa[8][D];
-    int rank[8];
-    // In place.  The mix is a real matrix, so the real and the imaginary parts of the bin are two
-    // independent real products: they are done one after the other with one set of D accumulators,
-    // which keeps the live registers at ~3D doubles (x complex + y) instead of 5D.
-    __device__ __forceinline__ void apply(const double* f, int Q, cplx* x) const {
-        double ks[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) ks[d] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (q < Q) {   // warp-uniform
-#pragma unroll
-                for (int d = 0; d < D; ++d) ks[d] = fma(f[q], kappa[q][d], ks[d]);
-            }
-        }
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            double y[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) y[d] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (q < Q) {   // warp-uniform
-#pragma unroll
-                    for (int r = 0; r < kMaxRankPerKernel; ++r) {
-                        if (r < rank[q]) {   // warp-uniform
-                            double t = 0.0;
-#pragma unroll
-                            for (int d = 0; d < D; ++d) t = fma(a[q][r][d], part ? x[d].y : x[d].x, t);
-                            t *= f[q];
-#pragma unroll
-                            for (int d = 0; d < D; ++d) y[d] = fma(a[q][r][d], t, y[d]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                if (part) x[d].y = fma(ks[d], x[d].y, y[d]);
-                else x[d].x = fma(ks[d], x[d].x, y[d]);
-            }
-        }
-    }
-};
-
-struct FusedArgs {
-    cplx* data;
-    long slab_stride, line_stride;
-    int n_lines, L, valid, lpc;   // lines per slab, line length, valid prefix, line-sets per CTA
-    int Q;
-    const double* specL;          // [Q][n_lines][L]
-    const cplx* stage_tw;         // per-stage twiddle tables (global), layout `lay`
-    int tw_total;
-    StageTw lay;
-    FftPlan plan;
-    int pitch, half;
-};
-
-template <int D, class MIX>
-__global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, const MIX mb) {
+// Forward row pass, software pipelined over `spc` consecutive slabs per CTA: while the rows of one
+// slab go through their shared-memory stages and the transposed store, the global loads of the next
+// slab's rows are already in flight in registers (the plain kernel was bound by exposed DRAM latency:
+// ~40 % of the HBM rate at 24 % occupancy, L2 hit rate ~0).
+template <int R0>
+__global__ void __launch_bounds__(256) fft_rows_T_fwd_pipe_kernel(const RowsTArgs a, int spc, int nslab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tws = reinterpret_cast<cplx*>(smem_raw);            // per-stage twiddle tables
-    cplx* tile = tws + a.tw_total;                            // [lpc*D][pitch]
-    const int L = a.L, pitch = a.pitch, lpc = a.lpc;
-    const int lL = 31 - __clz(L);
-    const int line0 = blockIdx.x * lpc;
-    const long pair = blockIdx.y;
-    cplx* base = a.data + pair * D * a.slab_stride;
-    const int nl = lpc * D;
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    cplx* tws = reinterpret_cast<cplx*>(smem_raw);
+    cplx* tile = tws + a.tw_total;
+    const int L = a.mty, nr = a.nr, pitch = a.pitch;
+    const int x0 = blockIdx.x * nr;
+    const int warp = threadIdx.x >> 5;            // one warp per row: blockDim.x == 32 * nr
+    const long slab0 = (long)blockIdx.y * spc;
+    const int cnt = (int)min((long)spc, (long)nslab - slab0);
+    const int valid = (x0 + warp < a.mx) ? a.my : 0;
+    const cplx* grow = a.G_in + slab0 * a.g_slab + (long)(x0 + warp) * a.my;
+    FirstStageRegs<R0, 2> f;
+    first_stage_load<R0, 2>(f, grow, valid, L);
     for (int i = threadIdx.x; i < a.tw_total; i += blockDim.x) tws[i] = a.stage_tw[i];
     __syncthreads();
-    for (int li = warp; li < nl; li += nwarps) {
-        const int ll = li / D, d = li - ll * D;
-        if (line0 + ll >= a.n_lines) continue;
-        const cplx* g = base + d * a.slab_stride + (long)(line0 + ll) * a.line_stride;
-        warp_fft_forward(g, a.valid, tile + li * pitch, L, a.plan, a.lay, tws, a.half != 0);
-    }
-    __syncthreads();
-    // ---- mix:  y[dp] = sum_d (sum_q f_q B_q[dp][d]) x[d]  at every bin of every line-set ----
-    for (int w = threadIdx.x; w < lpc * L; w += blockDim.x) {
-        const int ll = w >> lL, p = w & (L - 1);
-        if (line0 + ll >= a.n_lines) continue;
-        cplx* col = tile + (ll * D) * pitch + pad_idx(p);
-        cplx x[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = col[d * pitch];
-        double f[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            f[q] = (q < a.Q) ? __ldg(&a.specL[((long)q * a.n_lines + line0 + ll) * L + p]) : 0.0;
-        mb.apply(f, a.Q, x);
-#pragma unroll
-        for (int d = 0; d < D; ++d) col[d * pitch] = x[d];
-    }
-    __syncthreads();
-    for (int li = warp; li < nl; li += nwarps) {
-        const int ll = li / D, d = li - ll * D;
-        if (line0 + ll >= a.n_lines) continue;
-        cplx* g = base + d * a.slab_stride + (long)(line0 + ll) * a.line_stride;
-        warp_fft_inverse(tile + li * pitch, L, a.plan, a.lay, tws, a.half != 0, g, a.valid);
+    cplx* line = tile + warp * pitch;
+    for (int t = 0; t < cnt; ++t) {
+        first_stage_compute<R0, 2>(f, line, L, tws + a.lay.off[0]);
+        if (t + 1 < cnt) first_stage_load<R0, 2>(f, grow + (long)(t + 1) * a.g_slab, valid, L);
+        warp_fft_forward_rest(line, L, a.plan, a.lay, tws);
+        __syncthreads();
+        cplx* st = a.ST + (slab0 + t) * a.st_slab;
+        for (int idx = threadIdx.x; idx < L * nr; idx += blockDim.x) {
+            const int e = idx >> a.lnr, l = idx & (nr - 1);
+            st[(long)e * a.xpitch + x0 + l] = tile[l * pitch + pad_idx(e)];
+        }
+        __syncthreads();
     }
 }
 
@@ -626,63 +513,13 @@ __global__ void stage_twiddle_kernel(cplx* tab, int L, FftPlan pl, StageTw lay) 
     }
 }
 
-static const size_t kFusedSmemMax = 200 * 1024;
-
-template <int D>
-static int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, int npairs,
-                              cudaStream_t st) {
-    static MixB<D> mb;   // zero-initialised; only the first Q blocks are read
-    static MixLR<D> ml;
-    int total_rank = 0, max_rank = 0;
-    if (mix.ranks)
-        for (int q = 0; q < a.Q; ++q) {
-            total_rank += mix.ranks[q];
-            max_rank = std::max(max_rank, mix.ranks[q]);
-        }
-    const bool lowrank = mix.ranks && max_rank <= kMaxRankPerKernel &&
-                         total_rank * (4 * D + 2) + (a.Q + 2) * D < (a.Q + 2) * D * D;
-    if (lowrank) {
-        int r = 0;
-        for (int q = 0; q < a.Q; ++q) {
-            ml.rank[q] = mix.ranks[q];
-            for (int k = 0; k < mix.ranks[q]; ++k, ++r)
-                for (int d = 0; d < D; ++d) ml.a[q][k][d] = mix.A[(size_t)r * D + d];
-            for (int d = 0; d < D; ++d) ml.kappa[q][d] = mix.kappa[(size_t)q * D + d];
-        }
-    } else {
-        for (int q = 0; q < a.Q; ++q)
-            for (int i = 0; i < D; ++i)
-                for (int j = 0; j < D; ++j) mb.b[q][i][j] = mix.B[((size_t)q * D + i) * D + j];
-    }
-    a.plan = make_plan(a.L);
-    a.lay = stage_tw_layout(a.L, a.plan);
-    a.tw_total = a.lay.total;
-    a.stage_tw = stage_tw;
-    a.pitch = line_pitch(a.L);
-    a.half = (a.L >= 2 && a.valid <= a.L / 2) ? 1 : 0;
-    const size_t per_set = (size_t)D * a.pitch * sizeof(cplx);
-    int lpc = (int)std::max<size_t>(1, std::min<size_t>(48 * 1024 / per_set, (size_t)(4096 / (D * a.L) + 1)));
-    lpc = std::max(1, std::min(lpc, a.n_lines));
-    a.lpc = lpc;
-    const size_t smem = per_set * lpc + sizeof(cplx) * (size_t)a.tw_total;
-    LMC_REQUIRE(smem <= kFusedSmemMax, "fused spectral tile does not fit shared memory");
-    static bool attr = false;
-    if (!attr) {
-        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MixB<D>>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
-        LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MixLR<D>>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
-        attr = true;
-    }
-    const int threads = 32 * std::max(2, std::min(10, lpc * D));   // one warp per line, up to 10 warps
-    dim3 grid((unsigned)ceil_div(a.n_lines, lpc), (unsigned)npairs);
-    ProfScope prof(PROF_MIX, st);
-    if (lowrank) fused_lines_kernel<D, MixLR<D>><<<grid, threads, smem, st>>>(a, ml);
-    else fused_lines_kernel<D, MixB<D>><<<grid, threads, smem, st>>>(a, mb);
-    count_launch();
-    LMC_CHECK(cudaGetLastError());
-    return 0;
-}
+}  // namespace lmc
+#include "spectral_fused.cuh"
+namespace lmc {
+LMC_FUSED_EXTERN(1) LMC_FUSED_EXTERN(2) LMC_FUSED_EXTERN(3) LMC_FUSED_EXTERN(4)
+LMC_FUSED_EXTERN(5) LMC_FUSED_EXTERN(6) LMC_FUSED_EXTERN(7) LMC_FUSED_EXTERN(8)
+LMC_FUSED_EXTERN(9) LMC_FUSED_EXTERN(10) LMC_FUSED_EXTERN(11) LMC_FUSED_EXTERN(12)
+LMC_FUSED_EXTERN(13) LMC_FUSED_EXTERN(14) LMC_FUSED_EXTERN(15) LMC_FUSED_EXTERN(16)
 
 // ---------------------------------------------------------------------------
 // SpectralEngine
@@ -980,7 +817,24 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         dim3 grid((unsigned)(xpitch / r.nr), (unsigned)(npairs * D));
         {
             ProfScope prof(PROF_FFT_FWD_CONTIG, st);
-            fft_rows_T_kernel<false><<<grid, threads, smem, st>>>(r);
+            const int R0 = r.plan.radix[0];
+            const int nslab = npairs * D;
+            if (e.mt[1] / R0 <= 64 && (long)(xpitch / r.nr) * ceil_div(nslab, 4) >= 148 * 4) {   // <= 2 first-stage butterflies per lane
+                static bool attr_p = false;
+                if (!attr_p) {
+                    LMC_CHECK(cudaFuncSetAttribute(fft_rows_T_fwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
+                    LMC_CHECK(cudaFuncSetAttribute(fft_rows_T_fwd_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
+                    LMC_CHECK(cudaFuncSetAttribute(fft_rows_T_fwd_pipe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
+                    attr_p = true;
+                }
+                const int spc = 4;
+                dim3 gridp((unsigned)(xpitch / r.nr), (unsigned)ceil_div(nslab, spc));
+                if (R0 == 8) fft_rows_T_fwd_pipe_kernel<8><<<gridp, threads, smem, st>>>(r, spc, nslab);
+                else if (R0 == 4) fft_rows_T_fwd_pipe_kernel<4><<<gridp, threads, smem, st>>>(r, spc, nslab);
+                else fft_rows_T_fwd_pipe_kernel<2><<<gridp, threads, smem, st>>>(r, spc, nslab);
+            } else {
+                fft_rows_T_kernel<false><<<grid, threads, smem, st>>>(r);
+            }
             count_launch();
             LMC_CHECK(cudaGetLastError());
         }

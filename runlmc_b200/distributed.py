@@ -51,12 +51,19 @@ def sharded_gradient(fused, y, probes, kernel_grad_tops, coreg_vecs, coreg_mats,
     from .fused import assemble_gradients
     N = len(probes)
     lo, hi = shard_bounds(N, rank, world)
+    import torch
     local = np.asarray(probes[lo:hi], dtype=np.float64)
-    RHS = np.vstack([np.asarray(y, dtype=np.float64).reshape(1, -1), local])
-    X, iters, resid, _ = fused.minres(RHS, tol=tol)
-    alpha, inv = X[0], X[1:]
+    # one upload of [y; local probes]; the solutions stay on the device for the Gram stage
+    dev = torch.device('cuda', torch.cuda.current_device())
+    RHS = torch.empty((1 + len(local), fused.n), dtype=torch.float64, device=dev)
+    RHS[0].copy_(torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64).reshape(-1)))
+    if len(local):
+        RHS[1:].copy_(torch.as_tensor(np.ascontiguousarray(local)))
+    X, iters, resid, _ = fused.minres_device(RHS, tol=tol)
     extra = [t for ts in kernel_grad_tops for t in ts]
-    quad, trace, nquad, ntrace = fused.grad_grams(alpha, local, inv, extra)
+    quad, trace, nquad, ntrace = fused.grad_grams_device(
+        X[0], RHS[1:] if len(local) else None, X[1:] if len(local) else None, extra)
+    alpha = X[0].cpu().numpy()
     it_sum = float(np.sum(iters[1:])) + (float(iters[0]) if rank == 0 else 0.0)
     rs_sum = float(np.sum(resid[1:])) + (float(resid[0]) if rank == 0 else 0.0)
     trace, ntrace, it_sum, rs_sum = allreduce_trace(trace, ntrace, it_sum, rs_sum, group)

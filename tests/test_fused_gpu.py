@@ -247,6 +247,25 @@ def test_gradient_against_reference_golden(name):
     assert rel_err(nz, g['g_noise']) < GRAD_TOL
 
 
+@pytest.mark.parametrize('name', ['lmc_B', 'lmc_2d'])
+def test_sharded_gradient_single_rank(name):
+    """The whole gradient evaluation (device-resident solves + Gram stage + chain rule) through
+    distributed.sharded_gradient with one rank; the golden solves stopped at the same iterates the
+    reference's did, so gradients agree to the solver tolerance, not to GRAD_TOL."""
+    from test_oracle_golden import GOLDEN_PROBLEMS
+    from runlmc_b200.distributed import sharded_gradient
+    g = load_golden(name)
+    prob = GOLDEN_PROBLEMS[name]()
+    op = fused_from_problem(prob)
+    grads, stats = sharded_gradient(op, prob.y, g['probes'], prob.top_grads, prob.coreg_vecs,
+                                    prob.coreg_mats(), tol=1e-4)
+    assert rel_err(stats['alpha'], g['alpha']) < 10 * SOLVE_TOL
+    assert rel_err(np.array(grads[0]), g['g_coreg_vec']) < 1e-3
+    assert rel_err(np.array(grads[1]), g['g_coreg_diag']) < 1e-3
+    assert rel_err(np.array(grads[2]), g['g_kernel']) < 1e-3
+    assert rel_err(grads[3], g['g_noise']) < 1e-3
+
+
 def test_error_paths():
     from runlmc_b200.fused import FusedLMC
     prob = PROBLEMS['A']()
