@@ -698,3 +698,88 @@ def flatten_gradients(g):
     parts += [np.asarray(k, dtype=float) for k in g['kernel']]
     parts.append(np.ravel(g['noise']))
     return np.concatenate(parts)
+
+
+# ---------------------------------------------------------------------------
+# Prediction (runlmc/models/interpolated_llgp.py:293-397) -- the model class
+# itself needs paramz, so its arithmetic is restated here on the oracle
+# operator; one active-dimension group (the fused path's case).
+# ---------------------------------------------------------------------------
+
+def exact_cross_kernel(spec, Xs, Zs):
+    """ExactLMCLikelihood.kernel_from_indices (lmc/likelihood.py:183-203):
+    dense K[i, j] = sum_q B_q[out(i), out(j)] k_q(|x_i - z_j|), no noise."""
+    import scipy.spatial.distance as dist
+    rlens, clens = [len(X) for X in Xs], [len(Z) for Z in Zs]
+    X = np.vstack([np.asarray(x, dtype=float).reshape(len(x), -1) for x in Xs])
+    Z = np.vstack([np.asarray(z, dtype=float).reshape(len(z), -1) for z in Zs])
+    r = dist.cdist(X, Z)
+    rb = np.concatenate([[0], np.cumsum(rlens)])
+    cb = np.concatenate([[0], np.cumsum(clens)])
+    K = np.zeros(r.shape)
+    for B, kind, kp in zip(spec.coreg_mats(), spec.kinds, spec.kparams):
+        Kq = kern_eval(kind, kp, r)
+        for i in range(len(rlens)):
+            for j in range(len(clens)):
+                Kq[rb[i]:rb[i + 1], cb[j]:cb[j + 1]] *= B[i, j]
+        K += Kq
+    return K
+
+
+def native_variance(spec):
+    """_native_variance (interpolated_llgp.py:304-316): prior variance of one
+    point of each output, sum_q (|a_q[:, d]|^2 + kappa_q[d]) k_q(0) + noise_d."""
+    coregs = np.column_stack([np.square(np.atleast_2d(a)).sum(axis=0)
+                              for a in spec.coreg_vecs])
+    coregs = coregs + np.column_stack(spec.coreg_diags)
+    k0 = np.array([kern_eval(kind, kp, np.zeros(1))[0]
+                   for kind, kp in zip(spec.kinds, spec.kparams)])
+    return coregs.dot(k0).reshape(-1) + np.asarray(spec.noise)
+
+
+def predict_mean(op, alpha, Xs_test, grids):
+    """W* (K_UU W^T alpha); _grid_alpha + _raw_predict (interpolated_llgp.py:293-300, 334-338)."""
+    grid_alpha = op.grid_matvec(op.WT.dot(alpha))
+    Wt = multi_interpolant_csr(Xs_test, *grids)
+    return Wt.dot(grid_alpha)
+
+
+def precomputed_nu(op, tol=1e-4):
+    """_precomputed_nu / _var_solve (interpolated_llgp.py:350-388): for every grid
+    index i, nu_i = e_i' K_UX K^-1 K_XU e_i with K_XU = W K_UU."""
+    Dm = op.W.shape[1]
+    nu = np.zeros(Dm)
+    for i in range(Dm):
+        e = np.zeros(Dm)
+        e[i] = 1
+        x = op.W.dot(op.grid_matvec(e))
+        x, _, _ = iterative_solve(op.matvec, x, tol)
+        nu[i] = op.grid_matvec(op.WT.dot(x))[i]
+    return nu
+
+
+def predict_var_precompute(op, Xs_test, grids, nu):
+    """_var_predict_precompute (interpolated_llgp.py:384-388): W* nu."""
+    return multi_interpolant_csr(Xs_test, *grids).dot(nu)
+
+
+def predict_var_on_the_fly(op, spec, Xs_train, Xs_test, tol=1e-4):
+    """_var_predict_on_the_fly (interpolated_llgp.py:390-397): one solve per test
+    point with the exact cross-covariance row as right-hand side."""
+    Kx = exact_cross_kernel(spec, Xs_test, Xs_train)
+    inv = np.array([iterative_solve(op.matvec, k, tol)[0] for k in Kx]).T
+    return np.einsum('ij,ji->i', Kx, inv)
+
+
+def predict(op, spec, alpha, Xs_train, Xs_test, grids, mode='on-the-fly', tol=1e-4, nu=None):
+    """_raw_predict (interpolated_llgp.py:324-348): (mean, var), var clipped at 0."""
+    lens = [len(X) for X in Xs_test]
+    mean = predict_mean(op, alpha, Xs_test, grids)
+    nat = np.repeat(native_variance(spec), lens)
+    if mode == 'precompute':
+        expl = predict_var_precompute(op, Xs_test, grids, precomputed_nu(op, tol) if nu is None else nu)
+    else:
+        expl = predict_var_on_the_fly(op, spec, Xs_train, Xs_test, tol)
+    var = nat - expl
+    var[var < 0] = 0
+    return mean, var

@@ -506,6 +506,7 @@ struct Tile3Smem {
     int bin[BX][BY + 1];          // local offset of every bin of the window (+ end of row)
     int row_beg[BX];
     int row_off[BX + 1];
+    int live[64];                 // per group of this CTA: any column still active
 };
 
 template <int G, int TX, int TY, int CAP>
@@ -540,6 +541,9 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
         s.row_beg[tid] = beg;
         s.row_off[tid + 1] = end - beg;
     }
+    // one thread per group looks at the group's activity flags (instead of every thread, every group)
+    if (tid >= 64 && tid < 128 && grp0 + (tid - 64) < grp1)
+        s.live[tid - 64] = group_active(a, 2 * G * (grp0 + tid - 64), 2 * G) ? 1 : 0;
     __syncthreads();
     if (tid == 0) {
         s.row_off[0] = 0;
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
 
     for (int grp = grp0; grp < grp1; ++grp) {
         const int col0 = 2 * G * grp;
-        const bool live = group_active(a, col0, 2 * G);      // uniform over the CTA
+        const bool live = s.live[grp - grp0] != 0;           // uniform over the CTA
         if (live) {
             const int ncol = min(2 * G, a.ncols - col0);
             const double* gp = a.in + (long)col0 * a.ld;
@@ -753,6 +757,8 @@ struct Gather3Smem {
     cplx cell[2][GP][W * W];
     int row_beg[TB];
     int row_off[TB + 1];
+    double scale[272];           // per column of this CTA's pair range: in_scale (1 if none)
+    unsigned char act[272];      // ... and activity flag (0 also for columns past the block)
 };
 
 template <int GP, int TB>
@@ -781,6 +787,12 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
         s.row_beg[tid] = beg;
         s.row_off[tid + 1] = end - beg;
     }
+    for (int c = tid; c < 2 * (pair_hi - pair_lo) + 2 && c < 272; c += 256) {
+        const int col = 2 * pair_lo + c;
+        const bool in = col < a.ncols;
+        s.act[c] = (in && (!a.active || a.active[col])) ? 1 : 0;
+        s.scale[c] = (in && a.in_scale) ? a.in_scale[col] : 1.0;
+    }
     __syncthreads();
     if (tid == 0) {
         s.row_off[0] = 0;
@@ -794,7 +806,7 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
         for (int p = 0; p < GP; ++p) {
             const int pair = pbase + p;
             if (pair >= pair_hi) break;
-            if (!group_active(a, 2 * pair, 2)) continue;
+            if (!(s.act[2 * (pair - pair_lo)] | s.act[2 * (pair - pair_lo) + 1])) continue;
             const cplx* gsl = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
             // window cell (x, y) holds G[clamp(X0 + x)][clamp(Y0 + y)]: stencils index the window
             // without clamping and still pick up the edge cell for every clamped tap
@@ -844,8 +856,7 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
         for (int q = 0; q < 2; ++q) v[q][0] = v[q][1] = 0.0;
         if (!a.noise || pair >= pair_hi) return;
         const int cA = 2 * pair, cB = cA + 1;
-        const bool actA = !a.active || a.active[cA];
-        const bool actB = cB < a.ncols && (!a.active || a.active[cB]);
+        const bool actA = s.act[cA - 2 * pair_lo], actB = s.act[cB - 2 * pair_lo];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (!have[q]) continue;
@@ -867,13 +878,10 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
             if (pair >= pair_hi) break;
             fetch_in(pair + 1, nxt);
             const int cA = 2 * pair, cB = cA + 1;
-            const bool hasB = cB < a.ncols;
-            const bool actA = !a.active || a.active[cA];
-            const bool actB = hasB && (!a.active || a.active[cB]);
+            const bool actA = s.act[cA - 2 * pair_lo], actB = s.act[cB - 2 * pair_lo];
             if (actA || actB) {
                 const cplx* cl = s.cell[buf][p];
-                const double scA = a.in_scale ? a.in_scale[cA] : 1.0;
-                const double scB = (a.in_scale && hasB) ? a.in_scale[cB] : 1.0;
+                const double scA = s.scale[cA - 2 * pair_lo], scB = s.scale[cB - 2 * pair_lo];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     if (!have[q]) continue;
@@ -1019,7 +1027,7 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, boo
             const int ngroups = ceil_div(npairs, G);
             const long ctas1 = (long)a.tiles * ps.D;
             // all groups in one CTA (weights computed once) unless that leaves the machine underfilled
-            int gpc = ngroups;
+            int gpc = std::min(ngroups, 64);
             while (gpc > 1 && ctas1 * ceil_div(ngroups, gpc) < 148L * 2 * 4) gpc = (gpc + 1) / 2;
             dim3 grid3((unsigned)ctas1, (unsigned)ceil_div(ngroups, gpc));
             to_grid_2d_v3_kernel<G, TX, TY, CAP><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
@@ -1066,7 +1074,7 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
             a.tiles = ceil_div(ps.nb[0], TB) * a.tiles1;
             const long ctas1 = (long)a.tiles * ps.D;
             const int npass = ceil_div(npairs, GP);
-            int ppc = npass;
+            int ppc = std::min(npass, 272 / (2 * GP));
             while (ppc > 1 && ctas1 * ceil_div(npass, ppc) < 148L * 2 * 4) ppc = (ppc + 1) / 2;
             dim3 grid((unsigned)ctas1, (unsigned)ceil_div(npass, ppc));
             from_grid_2d_v3_kernel<GP, TB><<<grid, 256, sizeof(Smem), st>>>(a, ppc);

@@ -235,7 +235,87 @@ def lmc_case(prob, tol=1e-4, n_vec=3, reps=('sum', 'bt', 'slfm'),
     return out
 
 
+def predict_case(prob, n_test=7, tol=1e-4, seed=3):
+    """The three steps of InterpolatedLLGP._raw_predict (models/interpolated_llgp.py:293-397)
+    executed with the reference's own building blocks.  The model class itself cannot be imported
+    (paramz), so its glue is restated; every number below comes out of reference code:
+    multi_interpolant, GridKernel.grid_K.matvec, Composition/Matrix.wrap, Iterative.solve,
+    ExactLMCLikelihood.kernel_from_indices."""
+    from runlmc.lmc.likelihood import ExactLMCLikelihood
+    from runlmc.linalg.composition import Composition
+    from runlmc.linalg.matrix import Matrix
+    out = {}
+    fk = DuckKernel(prob)
+    ad = fk.ad
+    W = ref_interp.multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    dists = {ad: prob.dists}
+    K, _ = gen_grid_kernel(fk, dists, {ad: (W, WT)}, prob.lens)
+    rs = np.random.RandomState(seed)
+    Xs_test = [rs.uniform(0.05, 0.95, size=(n_test + d, prob.ndim)) for d in range(prob.D)]
+    lens = [len(X) for X in Xs_test]
+    alpha = Iterative.solve(K, prob.y, tol=tol)
+    # mean: interpolated_llgp.py:293-300, 334-338
+    grid_K = K.Ks[0].grid_K
+    grid_alpha = grid_K.matvec(WT.dot(alpha))
+    Wstar = ref_interp.multi_interpolant(Xs_test, *prob.grids)
+    mean = Wstar.dot(grid_alpha)
+    # native variance: interpolated_llgp.py:304-316
+    coregs = np.column_stack([np.square(a).sum(axis=0) for a in fk.coreg_vecs])
+    coregs = coregs + np.column_stack(fk.coreg_diags)
+    kernels = np.array([float(np.ravel(k)[0]) for k in fk.eval_kernels({ad: np.zeros(1)})])
+    native = np.repeat(coregs.dot(kernels).reshape(-1) + fk.noise, lens)
+    # on the fly: interpolated_llgp.py:390-397
+    fk.active_dims_list = None
+    K_test_X = ExactLMCLikelihood.kernel_from_indices(Xs_test, prob.Xs, _CdistKernel(fk, prob.ndim))
+    inverted = np.array([Iterative.solve(K, k, tol=tol) for k in K_test_X]).T
+    var_fly = native - np.diag(K_test_X.dot(inverted))
+    var_fly[var_fly < 0] = 0
+    # precompute: interpolated_llgp.py:350-388
+    K_XU = Composition([Matrix.wrap(W.shape, W.dot), grid_K])
+    K_UX = Composition([grid_K, Matrix.wrap(WT.shape, WT.dot)])
+    Dm = K_XU.shape[1]
+    nu = np.zeros(Dm)
+    for i in range(Dm):
+        x = np.zeros(Dm)
+        x[i] = 1
+        x = K_XU.matvec(x)
+        x = Iterative.solve(K, x, tol=tol)
+        nu[i] = K_UX.matvec(x)[i]
+    var_pre = native - Wstar.dot(nu)
+    var_pre[var_pre < 0] = 0
+    out.update(alpha=alpha, mean=mean, native=native, var_fly=var_fly, var_pre=var_pre, nu=nu,
+               K_test_X=K_test_X, lens=np.array(lens))
+    for d, X in enumerate(Xs_test):
+        out['Xtest_%d' % d] = X
+    return out
+
+
+class _CdistKernel:
+    """kernel_from_indices indexes inputs as Xs[:, active_dim] (likelihood.py:176-181); the duck
+    kernel's active-dim key is a tuple, which numpy treats as one index per axis -- expose the key as
+    a list instead so the column selection works for any input dimension."""
+
+    def __init__(self, fk, ndim):
+        self.fk, self.D = fk, fk.D
+        self.key = _ListKey(range(ndim))
+        self.active_dims = [self.key]
+
+    def eval_kernels(self, dists):
+        return self.fk.eval_kernels({self.fk.ad: dists[self.key]})
+
+    def coreg_mats(self):
+        return self.fk.coreg_mats()
+
+
+class _ListKey(list):
+    def __hash__(self):
+        return hash(tuple(self))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'predict':
+        return main_predict()
     np.savez_compressed(os.path.join(HERE, 'linalg.npz'), **linalg_cases())
     np.savez_compressed(os.path.join(HERE, 'interp.npz'), **interp_cases())
     # config A (README scale), 1-D, edge-touching inputs
@@ -253,6 +333,15 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'lmc_B.npz'),
                         **lmc_case(pb, reps=('sum',)))
     print('golden vectors written to', HERE)
+
+
+def main_predict():
+    pa = synthetic.make_problem('A', seed=1234, cells_per_lengthscale=4, grid=[40])
+    np.savez_compressed(os.path.join(HERE, 'predict_A.npz'), **predict_case(pa))
+    pe = synthetic.make_problem('e_small', seed=99, cells_per_lengthscale=3,
+                                lens=[60, 50, 55], grid=[8, 7], N=5)
+    np.savez_compressed(os.path.join(HERE, 'predict_2d.npz'), **predict_case(pe, n_test=5))
+    print('prediction golden vectors written to', HERE)
 
 
 if __name__ == '__main__':
