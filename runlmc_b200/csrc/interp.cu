@@ -378,27 +378,44 @@ __global__ void __launch_bounds__(256) from_grid_1d_v3_kernel(const InterpArgs a
     const int pair1 = min(npairs_tot, pair0 + pairs_per_cta);
     const cplx* gbase = a.Gc + (long)d * a.grid_pitch;
     const long pstride = (long)a.D * a.grid_pitch;
-#pragma unroll 2
-    for (int pair = pair0; pair < pair1; ++pair) {
-        const int cA = 2 * pair, cB = cA + 1;
-        const bool hasB = cB < a.ncols;
-        const bool actA = !a.active || a.active[cA];
-        const bool actB = hasB && (!a.active || a.active[cB]);
-        if (!actA && !actB) continue;
-        const cplx* gp = gbase + pair * pstride;
-        const cplx v0 = __ldg(gp + cell[0]), v1 = __ldg(gp + cell[1]);
-        const cplx v2 = __ldg(gp + cell[2]), v3 = __ldg(gp + cell[3]);
-        double inA = 0.0, inB = 0.0;
-        if (a.noise) {
-            if (actA) inA = a.in[(long)cA * a.ld + si];
-            if (actB) inB = a.in[(long)cB * a.ld + si];
-            if (a.in_scale) { inA *= a.in_scale[cA]; if (hasB) inB *= a.in_scale[cB]; }
+    // Chunks of CH pairs: all global loads of a chunk (inputs of the noise term and grid cells) are
+    // issued before its first store -- the compiler cannot hoist loads over stores to `out` (possible
+    // alias), and one pair at a time left the kernel waiting on DRAM (82 % long-scoreboard stalls).
+    constexpr int CH = 4;
+    for (int pc = pair0; pc < pair1; pc += CH) {
+        double inA[CH], inB[CH];
+        cplx v[CH][4];
+        bool actA[CH], actB[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int pair = pc + u;
+            const int cA = 2 * pair, cB = cA + 1;
+            const bool in_rng = pair < pair1;
+            actA[u] = in_rng && (!a.active || a.active[cA]);
+            actB[u] = in_rng && cB < a.ncols && (!a.active || a.active[cB]);
+            inA[u] = inB[u] = 0.0;
+            if (a.noise) {
+                if (actA[u]) inA[u] = a.in[(long)cA * a.ld + si];
+                if (actB[u]) inB[u] = a.in[(long)cB * a.ld + si];
+            }
+            if (actA[u] || actB[u]) {
+                const cplx* gp = gbase + pair * pstride;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[u][t] = __ldg(gp + cell[t]);
+            }
         }
-        double oA = fma(w[3], v3.x, fma(w[2], v2.x, fma(w[1], v1.x, w[0] * v0.x)));
-        double oB = fma(w[3], v3.y, fma(w[2], v2.y, fma(w[1], v1.y, w[0] * v0.y)));
-        if (a.noise) { oA = fma(nz, inA, oA); oB = fma(nz, inB, oB); }
-        if (actA) a.out[(long)cA * a.ldo + so] = oA;
-        if (actB) a.out[(long)cB * a.ldo + so] = oB;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            if (!actA[u] && !actB[u]) continue;
+            const int cA = 2 * (pc + u), cB = cA + 1;
+            double iA = inA[u], iB = inB[u];
+            if (a.noise && a.in_scale) { iA *= a.in_scale[cA]; if (cB < a.ncols) iB *= a.in_scale[cB]; }
+            double oA = fma(w[3], v[u][3].x, fma(w[2], v[u][2].x, fma(w[1], v[u][1].x, w[0] * v[u][0].x)));
+            double oB = fma(w[3], v[u][3].y, fma(w[2], v[u][2].y, fma(w[1], v[u][1].y, w[0] * v[u][0].y)));
+            if (a.noise) { oA = fma(nz, iA, oA); oB = fma(nz, iB, oB); }
+            if (actA[u]) a.out[(long)cA * a.ldo + so] = oA;
+            if (actB[u]) a.out[(long)cB * a.ldo + so] = oB;
+        }
     }
 }
 
