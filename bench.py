@@ -178,6 +178,10 @@ def family_bytes(family, prob, P, bins, gpitch):
         return 8.0 * n * P + 8.0 * d * n + slab * gpitch
     if family == 'from_grid':
         return 16.0 * n * P + 8.0 * d * n + slab * gpitch
+    if family == 'other':
+        # the two permutation passes of the caller-order product (caller -> sorted before the scatter,
+        # sorted -> caller after the gather): each reads and writes the block once, plus the index
+        return 2 * (16.0 * n * P + 4.0 * n)
     if d == 2:
         # fused 2-D path: row transforms G <-> S_T[ky][x] (only the m0 non-zero / kept x columns are
         # stored), column transform + mix + inverse in place on S_T

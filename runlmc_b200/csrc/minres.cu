@@ -146,13 +146,25 @@ __global__ void __launch_bounds__(kVecThreads) minres_k2_kernel(
     if (threadIdx.x == 0) part_b[(long)col * nblk + blockIdx.x] = acc;
 }
 
-// scalar recurrences after the Lanczos step (minres.py:236-283)
-__global__ void minres_s1_kernel(ColState* st, const int* active, const double* part_b, int nblk, int P) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= P || !active[col]) return;
+// fixed-order sum of `cnt` partials by one (small) block: strided per-thread sums, then a tree
+__device__ __forceinline__ double column_sum(const double* part, int cnt) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) v += part[i];
+    return block_reduce_sum(v);
+}
+
+static const int kScalarThreads = 64;   // threads per column in the scalar kernels (one block per column)
+
+// scalar recurrences after the Lanczos step (minres.py:236-283); one block per column so the sum of
+// the per-CTA partials is a parallel reduction (a single thread walking ~500 partials cost 40 us)
+__global__ void minres_s1_kernel(ColState* st, const int* active, const double* part_b, int nblk, int P,
+                                 int* n_active) {
+    const int col = blockIdx.x;
+    if (col == 0 && threadIdx.x == 0) *n_active = 0;   // recounted by the s2 kernel that follows
+    if (!active[col]) return;
+    const double s = column_sum(part_b + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
     ColState c = st[col];
-    double s = 0.0;
-    for (int i = 0; i < nblk; ++i) s += part_b[(long)col * nblk + i];
     c.itn += 1;
     c.oldb = c.beta;
     c.beta = sqrt(s);
@@ -211,41 +223,35 @@ __global__ void __launch_bounds__(kVecThreads) minres_k3_kernel(
     if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
 }
 
-// norms + stopping rules (minres.py:285-330); prepares the next step's scales
+// norms + stopping rules (minres.py:285-330); prepares the next step's scales.  One block per
+// column; the number of columns still running is an integer count (order independent).
 __global__ void minres_s2_kernel(ColState* st, double* inv_beta, int* active, const double* part_c, int nblk,
                                  int P, double rtol, int maxiter, int* n_active) {
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    for (int col = threadIdx.x; col < P; col += blockDim.x) {
-        if (active[col]) {
-            ColState c = st[col];
-            double s = 0.0;
-            for (int i = 0; i < nblk; ++i) s += part_c[(long)col * nblk + i];
-            const double ynorm = sqrt(s);
-            const double Anorm = sqrt(c.tnorm2);
-            const double epsx = Anorm * ynorm * DBL_EPSILON;
-            const double rnorm = c.phibar;
-            const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
-            const double test2 = (Anorm == 0.0) ? INFINITY : c.root / Anorm;
-            const double Acond = c.gmax / c.gmin;
-            if (c.istop == 0) {
-                if (1.0 + test2 <= 1.0) c.istop = 2;
-                if (1.0 + test1 <= 1.0) c.istop = 1;
-                if (c.itn >= maxiter) c.istop = 6;
-                if (Acond >= 0.1 / DBL_EPSILON) c.istop = 4;
-                if (epsx >= c.beta1) c.istop = 3;
-                if (test2 <= rtol) c.istop = 2;
-                if (test1 <= rtol) c.istop = 1;
-            }
-            c.c_r1 = c.beta / c.oldb;
-            if (c.istop != 0) { c.done = 1; active[col] = 0; }
-            else { inv_beta[col] = 1.0 / c.beta; atomicAdd(&s_cnt, 1); }
-            st[col] = c;
-        }
+    const int col = blockIdx.x;
+    if (!active[col]) return;
+    const double s = column_sum(part_c + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    ColState c = st[col];
+    const double ynorm = sqrt(s);
+    const double Anorm = sqrt(c.tnorm2);
+    const double epsx = Anorm * ynorm * DBL_EPSILON;
+    const double rnorm = c.phibar;
+    const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
+    const double test2 = (Anorm == 0.0) ? INFINITY : c.root / Anorm;
+    const double Acond = c.gmax / c.gmin;
+    if (c.istop == 0) {
+        if (1.0 + test2 <= 1.0) c.istop = 2;
+        if (1.0 + test1 <= 1.0) c.istop = 1;
+        if (c.itn >= maxiter) c.istop = 6;
+        if (Acond >= 0.1 / DBL_EPSILON) c.istop = 4;
+        if (epsx >= c.beta1) c.istop = 3;
+        if (test2 <= rtol) c.istop = 2;
+        if (test1 <= rtol) c.istop = 1;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *n_active = s_cnt;
+    c.c_r1 = c.beta / c.oldb;
+    if (c.istop != 0) { c.done = 1; active[col] = 0; }
+    else { inv_beta[col] = 1.0 / c.beta; atomicAdd(n_active, 1); }
+    st[col] = c;
 }
 
 // partial ||b - y||^2
@@ -268,26 +274,20 @@ __global__ void __launch_bounds__(kVecThreads) minres_resid_kernel(
     if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
 }
 
-// reference early termination (iterative.py:36-42): residual < tol stops the column
+// reference early termination (iterative.py:36-42): residual < tol stops the column.  One block per
+// column; *n_active must be zero on entry of a non-final pass.
 __global__ void minres_s3_kernel(ColState* st, int* active, const double* part, int nblk, int P, double tol,
                                  int final_pass, int* n_active) {
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    for (int col = threadIdx.x; col < P; col += blockDim.x) {
-        if (final_pass || active[col]) {
-            double s = 0.0;
-            for (int i = 0; i < nblk; ++i) s += part[(long)col * nblk + i];
-            const double r = sqrt(s);
-            st[col].resid = r;
-            if (!final_pass) {
-                if (r < tol) { st[col].istop = 10; st[col].done = 1; active[col] = 0; }
-                else atomicAdd(&s_cnt, 1);
-            }
-        }
+    const int col = blockIdx.x;
+    if (!final_pass && !active[col]) return;
+    const double s = column_sum(part + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    const double r = sqrt(s);
+    st[col].resid = r;
+    if (!final_pass) {
+        if (r < tol) { st[col].istop = 10; st[col].done = 1; active[col] = 0; }
+        else atomicAdd(n_active, 1);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && !final_pass) *n_active = s_cnt;
 }
 
 __global__ void __launch_bounds__(kVecThreads) minres_finish_kernel(
@@ -437,7 +437,7 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
         { double* t = r1; r1 = r2; r2 = y; y = t; }   // r1 <- r2 <- y ; old r1 buffer is the next y
         {
             ProfScope prof(PROF_MINRES_SCALAR, st);
-            minres_s1_kernel<<<sblocks, sthreads, 0, st>>>(cs, active, pb, nblk, P);
+            minres_s1_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pb, nblk, P, n_active);
         }
         {
             // v = r1 / oldb
@@ -447,7 +447,7 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
         { double* t = wa; wa = wb; wb = wc; wc = t; }
         {
             ProfScope prof(PROF_MINRES_SCALAR, st);
-            minres_s2_kernel<<<1, 256, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
+            minres_s2_kernel<<<P, kScalarThreads, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
         }
         count_launch(5);
         bool polled = false;
@@ -455,7 +455,8 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
             // reference callback: true residual of the columns still running
             LMC_TRY(A.apply(x, nullptr, active, y, P, st));
             minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, active, n, pa, nblk);
-            minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
+            LMC_CHECK(cudaMemsetAsync(n_active, 0, sizeof(int), st));
+            minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
             count_launch(2);
             polled = true;
         }
@@ -468,7 +469,7 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
     // final residual of every column (iterative.py:53)
     LMC_TRY(A.apply(x, nullptr, nullptr, y, P, st));
     minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, nullptr, n, pa, nblk);
-    minres_s3_kernel<<<1, 256, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
+    minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
     minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(x, perm, n, X, ld);
     count_launch(3);
     LMC_CHECK(cudaGetLastError());
