@@ -133,6 +133,76 @@ def test_linearity_and_symmetry_large():
     assert float(torch.dot(V[0], KV[0])) > 0
 
 
+@pytest.mark.parametrize('ndim', [2, 1])
+def test_wide_blocks_match_narrow_blocks_and_oracle(ndim):
+    """Block widths that exercise what the 4-column tests cannot: several 16-pair groups per CTA, the
+    odd pair(s) routed through the one-pair scatter kernel (33 = 2*16 + 1 pairs, 34 = 2*16 + 2), several
+    8-pair gather passes, more than one block of 128 pairs, the pipelined row pass (many slabs)."""
+    import torch
+    if ndim == 2:
+        # ~1.3 points per bin: the tiled scatter / gather kernels' capacities hold, like at config E
+        prob = synthetic.make_problem('E', seed=4, cells_per_lengthscale=5, lens=[4000, 3500, 3800],
+                                      D=3, grid=[64, 48], N=2)
+    else:
+        prob = synthetic.make_problem('D', seed=4, cells_per_lengthscale=5, lens=[9000, 7000, 8000],
+                                      D=3, grid=[1024], N=2)
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    rng = np.random.default_rng(2)
+    Pmax = 300
+    V = rng.standard_normal((Pmax, prob.n))
+    Vd = torch.as_tensor(V, device='cuda')
+    narrow = torch.cat([op.mvm_device(Vd[i:i + 4].contiguous()) for i in range(0, Pmax, 4)]).cpu().numpy()
+    for c in (0, 65, 66, 128, 299):
+        assert rel_err(narrow[c], ref.matvec(V[c])) < MVM_TOL
+    perm = op.perm()
+    for P in (65, 67, 129, 300):
+        wide = op.mvm_device(Vd[:P].contiguous()).cpu().numpy()
+        assert rel_err(wide, narrow[:P]) < 1e-12
+        assert max(rel_err(wide[c], narrow[c]) for c in range(P)) < 1e-12
+        Vs = torch.as_tensor(np.ascontiguousarray(V[:P][:, perm]), device='cuda')
+        wide_sorted = op.mvm_sorted_device(Vs).cpu().numpy()
+        assert max(rel_err(wide_sorted[c], narrow[c][perm]) for c in range(P)) < 1e-12
+    # host-buffer entry point on a wide block
+    assert rel_err(op.mvm(V[:67]), narrow[:67]) < 1e-12
+
+
+def test_wide_minres_matches_single_column_solves():
+    """Columns of a wide block stop at different iterations (activity masks inside the kernels);
+    every column must end where it ends when solved alone."""
+    prob = well_conditioned_problem()
+    op = fused_from_problem(prob)
+    rng = np.random.default_rng(3)
+    P = 35
+    RHS = rng.standard_normal((P, prob.n)) * np.logspace(-3, 1, P)[:, None]
+    RHS[7] = 0.0
+    X, iters, resid, istop = op.minres(RHS, tol=1e-4, check_every=5)
+    assert len(set(iters.tolist())) > 2                     # they really stop at different times
+    for c in (0, 7, 12, 33, 34):
+        x1, it1, r1, st1 = op.minres(RHS[c:c + 1], tol=1e-4, check_every=5)
+        assert it1[0] == iters[c] and st1[0] == istop[c]
+        # a column shares its complex FFT with its pair partner: ulp-level cross-talk through the
+        # twiddle products, amplified by Lanczos to ~1e-6 at convergence -- far inside the tolerance
+        assert rel_err(X[c], x1[0]) < SOLVE_TOL or np.all(x1[0] == 0)
+    assert np.all(resid < 1e-4)
+
+
+def test_wide_minres_2d():
+    prob = PROBLEMS['2d_small']()
+    prob.noise = np.full(prob.D, 25.0)
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    rng = np.random.default_rng(5)
+    P = 37
+    RHS = rng.standard_normal((P, prob.n)) * np.logspace(-2, 1, P)[:, None]
+    X, iters, resid, istop = op.minres(RHS, tol=1e-4, check_every=5)
+    for c in (0, 18, 35, 36):
+        xr, ctr, err = orc.iterative_solve(ref.matvec, RHS[c], 1e-4, check_every=5)
+        assert abs(int(iters[c]) - ctr) <= 5
+        assert rel_err(X[c], xr) < SOLVE_TOL
+    assert np.all(resid < 1e-4)
+
+
 # MINRES parity.  Lanczos amplifies ulp-level differences in the operator: the
 # reference run with two of its own equivalent representations ('sum' vs 'bt')
 # already differs by 1e-3..1e-1 in mid-convergence iterates (k ~ 25) on these
