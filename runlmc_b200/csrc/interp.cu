@@ -101,6 +101,7 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
             return (int)worst;
         };
         ps->max_tile_pts_8x8 = worst_window(8, 8);
+        ps->max_tile_pts_16x8 = worst_window(16, 8);
         // population of every 16 x 16 tile of bins (no halo) the tiled gather kernel hands to one CTA
         long worst = 0;
         for (int d = 0; d < D; ++d)
@@ -993,33 +994,69 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, bool one_pair_ctas,
-                          cudaStream_t st);
+// which 2-D scatter kernel a segment of RHS pairs goes through
+enum ScatterKind { SCATTER_AUTO, SCATTER_G16, SCATTER_G8, SCATTER_PAIR };
+
+static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, ScatterKind kind, cudaStream_t st);
+
+template <int G, int TX, int TY, int CAP>
+static int launch_strips(const PointSet& ps, InterpArgs a, int npairs, cudaStream_t st) {
+    typedef Tile3Smem<G, TX, TY, CAP> Smem;
+    static bool attr3 = false;
+    if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }
+    a.tiles1 = ceil_div(ps.m[1], TY);
+    a.tiles = ceil_div(ps.m[0], TX) * a.tiles1;
+    const int ngroups = ceil_div(npairs, G);
+    const long ctas1 = (long)a.tiles * ps.D;
+    // all groups in one CTA (weights computed once) unless that leaves the machine underfilled
+    int gpc = std::min(ngroups, 64);
+    while (gpc > 1 && ctas1 * ceil_div(ngroups, gpc) < 148L * 2 * 4) gpc = (gpc + 1) / 2;
+    dim3 grid3((unsigned)ctas1, (unsigned)ceil_div(ngroups, gpc));
+    to_grid_2d_v3_kernel<G, TX, TY, CAP><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
+    return 0;
+}
+
+static const int kCap16 = 304, kCap8 = 448;   // staged points per CTA: 8x8 tile (16 pair lanes), 16x8 tile (8 lanes)
 
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) {
     if (cv.ncols == 0) return 0;
     ProfScope prof(PROF_TO_GRID, st);
     const int npairs = (cv.ncols + 1) / 2;
-    // 2-D: a block of 16 k + 1 (or + 2) pairs -- y plus an even number of probes -- would spend a whole
-    // 16-lane group pass of the strip kernel on the odd pair(s); they go through the
-    // one-pair-per-CTA kernel instead.
-    const int rem = npairs % 16;
-    if (ps.ndim == 2 && npairs > 16 && rem >= 1 && rem <= 2) {
-        const int head_pairs = npairs - rem;
-        ColumnView head = cv, tail = cv;
-        head.ncols = 2 * head_pairs;
-        tail.ncols = cv.ncols - 2 * head_pairs;
-        tail.in = cv.in + (long)2 * head_pairs * cv.ld;
-        tail.in_scale = cv.in_scale ? cv.in_scale + 2 * head_pairs : nullptr;
-        tail.active = cv.active ? cv.active + 2 * head_pairs : nullptr;
-        LMC_TRY(to_grid_launch(ps, head, G, false, st));
-        return to_grid_launch(ps, tail, G + (size_t)head_pairs * ps.D * ps.grid_pitch, true, st);
+    static const int variant = env_int("LMC_TOGRID2D", 3);
+    if (ps.ndim != 2 || variant < 3 || ps.max_tile_pts_8x8 > kCap16)
+        return to_grid_launch(ps, cv, G, SCATTER_AUTO, st);
+    // 2-D: the strip kernel's lanes are RHS pairs, 16 per group.  A block whose pair count is not a
+    // multiple of 16 (y plus an even number of probes; the 8 or 9 pairs a rank holds when 128 probes
+    // are sharded over 8 GPUs) would idle the lanes of its last group, so the remainder is split off:
+    // up to 8 pairs go through the 8-lane variant (16x8-cell tiles), one or two left-over pairs through
+    // the one-pair-per-CTA kernel.
+    const bool g8_ok = ps.max_tile_pts_16x8 <= kCap8;
+    struct Seg { int first, count; ScatterKind kind; };
+    Seg segs[3];
+    int nseg = 0;
+    int done = npairs / 16 * 16, rem = npairs - done;
+    if (done) segs[nseg++] = {0, done, SCATTER_G16};
+    if (rem >= 3 && rem <= 10 && g8_ok) {
+        // 9 or 10 pairs: the second 8-lane group (1 or 2 live lanes) reuses the CTA's staged weights,
+        // which is cheaper than a separate launch of the one-pair kernel
+        segs[nseg++] = {done, rem, SCATTER_G8};
+        done += rem; rem = 0;
     }
-    return to_grid_launch(ps, cv, G, false, st);
+    if (rem >= 1 && rem <= 2 && done > 0) segs[nseg++] = {done, rem, SCATTER_PAIR};
+    else if (rem) segs[nseg++] = {done, rem, SCATTER_G16};
+    for (int i = 0; i < nseg; ++i) {
+        ColumnView part = cv;
+        const int c0 = 2 * segs[i].first;
+        part.ncols = std::min(2 * segs[i].count, cv.ncols - c0);
+        part.in = cv.in + (long)c0 * cv.ld;
+        part.in_scale = cv.in_scale ? cv.in_scale + c0 : nullptr;
+        part.active = cv.active ? cv.active + c0 : nullptr;
+        LMC_TRY(to_grid_launch(ps, part, G + (size_t)segs[i].first * ps.D * ps.grid_pitch, segs[i].kind, st));
+    }
+    return 0;
 }
 
-static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, bool one_pair_ctas,
-                          cudaStream_t st) {
+static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, ScatterKind kind, cudaStream_t st) {
     InterpArgs a = make_args(ps, cv);
     a.G = G;
     const int npairs = (cv.ncols + 1) / 2;
@@ -1032,31 +1069,18 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, boo
         a.tiles = ceil_div(ps.m[0], TC);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
         to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
+    } else if (kind == SCATTER_G16) {
+        LMC_TRY((launch_strips<16, 8, 8, kCap16>(ps, a, npairs, st)));
+    } else if (kind == SCATTER_G8) {
+        LMC_TRY((launch_strips<8, 16, 8, kCap8>(ps, a, npairs, st)));
     } else {
-        static const int variant = env_int("LMC_TOGRID2D", 3);
-        constexpr int G = 16, TX = 8, TY = 8, CAP = 304;
-        if (variant >= 3 && !one_pair_ctas && ps.max_tile_pts_8x8 <= CAP) {
-            typedef Tile3Smem<G, TX, TY, CAP> Smem;
-            static bool attr3 = false;
-            if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }
-            a.tiles1 = ceil_div(ps.m[1], TY);
-            a.tiles = ceil_div(ps.m[0], TX) * a.tiles1;
-            const int ngroups = ceil_div(npairs, G);
-            const long ctas1 = (long)a.tiles * ps.D;
-            // all groups in one CTA (weights computed once) unless that leaves the machine underfilled
-            int gpc = std::min(ngroups, 64);
-            while (gpc > 1 && ctas1 * ceil_div(ngroups, gpc) < 148L * 2 * 4) gpc = (gpc + 1) / 2;
-            dim3 grid3((unsigned)ctas1, (unsigned)ceil_div(ngroups, gpc));
-            to_grid_2d_v3_kernel<G, TX, TY, CAP><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
-        } else {
-            a.tiles1 = ceil_div(ps.m[1], kTY);
-            a.tiles = ceil_div(ps.m[0], kTX) * a.tiles1;
-            dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)npairs);
-            const size_t smem = sizeof(double) * 32 * kBX * kBY;
-            static bool attr = false;
-            if (!attr) { LMC_TRY(set_smem(to_grid_2d_kernel, smem)); attr = true; }
-            to_grid_2d_kernel<<<grid, 384, smem, st>>>(a);
-        }
+        a.tiles1 = ceil_div(ps.m[1], kTY);
+        a.tiles = ceil_div(ps.m[0], kTX) * a.tiles1;
+        dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)npairs);
+        const size_t smem = sizeof(double) * 32 * kBX * kBY;
+        static bool attr = false;
+        if (!attr) { LMC_TRY(set_smem(to_grid_2d_kernel, smem)); attr = true; }
+        to_grid_2d_kernel<<<grid, 384, smem, st>>>(a);
     }
     count_launch();
     LMC_CHECK(cudaGetLastError());

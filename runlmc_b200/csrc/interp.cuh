@@ -15,6 +15,7 @@ struct PointSet {
     long grid_pitch = 0;  // cells allocated per (pair, output) slab
     bool identity = false;  // sorted order == caller's order
     int max_tile_pts_8x8 = 0;     // 2-D: most points in the 11x11 bins around an 8x8-cell scatter tile
+    int max_tile_pts_16x8 = 0;    // 2-D: same for the 19x11 bins around a 16x8-cell tile
     int max_gather_tile_pts = 0;  // 2-D: most points in a 16x16-bin gather tile
     int* perm = nullptr;     // [n] sorted position -> caller's index
     int* iperm = nullptr;    // [n] caller's index -> sorted position (nullptr when identity)
