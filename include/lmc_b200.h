@@ -54,6 +54,13 @@ int lmc_profile_end(double* ms, int* counts);
  * ndim is 1 or 2, D <= 16.  The X-dependent sort is done here, once.          */
 int lmc_op_create(lmc_op** out, int D, int ndim, const int* grid_sizes, const double* origin,
                   const double* delta, const int* lens, const double* X_host);
+/* Same operator from coordinates that already are on the device (X_dev [n][ndim]): base indices,
+ * fractional offsets, the stable sort by (output, grid bin) and the bin offsets are computed on the
+ * device -- the work of multi_interpolant (interpolation.py:119-176; 4 s on the host at n = 1M) without
+ * building a CSR.  The result is identical, bit for bit, to lmc_op_create on the same coordinates.
+ * Synchronises `stream` before returning.                                                          */
+int lmc_op_create_dev(lmc_op** out, int D, int ndim, const int* grid_sizes, const double* origin,
+                      const double* delta, const int* lens, const double* X_dev, void* stream);
 int lmc_op_destroy(lmc_op* op);
 /* Per-optimiser-step update.  tops_host [Q][prod grid_sizes]: kernel values
  * k_q(|z - z_0|) on the grid (grid_kernel.py:26-27); B_host [Q][D][D]:
@@ -66,6 +73,23 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
  * of O(D^2) per frequency bin.  Results are unchanged up to rounding.                         */
 int lmc_op_set_coreg_factors(lmc_op* op, const int* ranks_host, const double* A_host,
                              const double* kappa_host);
+/* Per-optimiser-step update with the kernel values evaluated on the device instead of uploaded:
+ * kinds_host[Q] in LMC_KERN_*, kparams_host[Q][2] = (inv_lengthscale, period; period ignored unless
+ * periodic).  k_q is evaluated at r = ||z - z_0|| of the operator's own grid (interpolated_llgp.py:431):
+ *   LMC_KERN_RBF           exp(-gamma r^2 / 2)                        (kern/rbf.py:39-40)
+ *   LMC_KERN_MATERN32      (1 + sqrt3 gamma r) exp(-sqrt3 gamma r)    (kern/matern32.py:39-41)
+ *   LMC_KERN_STD_PERIODIC  exp(-gamma sin^2(pi r / T) / 2)            (kern/std_periodic.py:44-48)
+ * followed by everything lmc_op_set_params does.  The descriptors are remembered for
+ * lmc_grad_grams_kernels; lmc_op_set_params forgets them.                                          */
+enum { LMC_KERN_RBF = 0, LMC_KERN_MATERN32 = 1, LMC_KERN_STD_PERIODIC = 2 };
+int lmc_op_set_kernels(lmc_op* op, int Q, const int* kinds_host, const double* kparams_host,
+                       const double* B_host, const double* noise_host);
+/* The tops the device evaluates for the remembered descriptors, copied to the host (tests,
+ * materialized_kernels): deriv == 0: the Q kernels [Q][m]; deriv != 0: their parameter derivatives
+ * [sum_q p_q][m] in kernel order (kernel_gradient of kern/rbf.py:50-54, matern32.py:50-57,
+ * std_periodic.py:58-67).  lmc_op_num_kernel_tops gives the first dimension.                       */
+int lmc_op_num_kernel_tops(const lmc_op* op, int deriv);
+int lmc_op_kernel_tops(lmc_op* op, int deriv, double* tops_host);
 long lmc_op_n(const lmc_op* op);          /* total points */
 long lmc_op_grid_cells(const lmc_op* op); /* m = prod grid_sizes */
 long lmc_op_embed_bins(const lmc_op* op); /* prod of the power-of-two embedding sizes */
@@ -130,6 +154,12 @@ int lmc_grad_grams(lmc_op* op, const double* alpha_dev, const double* R_dev, con
                    long ld, int N, int ntops_extra, const double* tops_extra_host,
                    double* quad_host, double* trace_host, double* nquad_host, double* ntrace_host,
                    void* stream);
+
+/* Same with the derivative tops d k_q / d theta evaluated on the device from the descriptors of
+ * lmc_op_set_kernels: T = Q + lmc_op_num_kernel_tops(op, 1).                                       */
+int lmc_grad_grams_kernels(lmc_op* op, const double* alpha_dev, const double* R_dev, const double* RINV_dev,
+                           long ld, int N, double* quad_host, double* trace_host, double* nquad_host,
+                           double* ntrace_host, void* stream);
 
 /* ---- stand-alone structured operators (runlmc/linalg mirror) ----------------
  * lmc_bttb: BTTB(top, sizes).matvec (bttb.py:91-148), ndim <= 3; ndim == 1 also

@@ -41,7 +41,12 @@ SIGNATURES = {
     'lmc_profile_begin': (_i, []),
     'lmc_profile_end': (_i, [_p, _p]),
     'lmc_op_create': (_i, [ctypes.POINTER(_p), _i, _i, _p, _p, _p, _p, _p]),
+    'lmc_op_create_dev': (_i, [ctypes.POINTER(_p), _i, _i, _p, _p, _p, _p, _p, _p]),
     'lmc_op_destroy': (_i, [_p]),
+    'lmc_op_set_kernels': (_i, [_p, _i, _p, _p, _p, _p]),
+    'lmc_op_num_kernel_tops': (_i, [_p, _i]),
+    'lmc_op_kernel_tops': (_i, [_p, _i, _p]),
+    'lmc_grad_grams_kernels': (_i, [_p, _p, _p, _p, _l, _i, _p, _p, _p, _p, _p]),
     'lmc_op_set_params': (_i, [_p, _i, _p, _p, _p]),
     'lmc_op_set_coreg_factors': (_i, [_p, _p, _p, _p]),
     'lmc_op_n': (_l, [_p]),

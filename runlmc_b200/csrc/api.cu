@@ -16,6 +16,46 @@ struct HostBlock {  // device staging for the *_host entry points
 };
 }  // namespace
 
+namespace lmc {
+
+// Spectra of the Q tops (already on the device), B and noise upload: everything a new set of
+// hyper-parameters changes.  Shared by lmc_op_set_params (host tops) and lmc_op_set_kernels
+// (tops evaluated on the device, setup.cu).
+int op_set_params_dev(lmc_op* op, int Q, const double* top_dev, const double* B_host, const double* noise_host) {
+    const long bins = op->emb.bins, cells = op->emb.cells;
+    const int D = op->D;
+    if (Q > op->spec_cap) {
+        cudaFree(op->spec); cudaFree(op->B); cudaFree(op->specL);
+        op->spec = nullptr; op->B = nullptr; op->specL = nullptr; op->spec_cap = 0;
+        LMC_CHECK(cudaMalloc(&op->spec, sizeof(double) * (size_t)Q * bins));
+        LMC_CHECK(cudaMalloc(&op->specL, sizeof(double) * (size_t)Q * bins));
+        LMC_CHECK(cudaMalloc(&op->B, sizeof(double) * (size_t)Q * D * D));
+        op->spec_cap = Q;
+    }
+    if (!op->noise) LMC_CHECK(cudaMalloc(&op->noise, sizeof(double) * D));
+    cplx* work = nullptr;
+    LMC_CHECK(cudaMalloc(&work, sizeof(cplx) * (size_t)bins));
+    int rc = 0;
+    cudaError_t e = cudaMemcpy(op->B, B_host, sizeof(double) * (size_t)Q * D * D, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(op->noise, noise_host, sizeof(double) * D, cudaMemcpyHostToDevice);
+    for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q)
+        rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
+    op->fused = op->eng.fused_supported(D, Q) && getenv("LMC_NO_FUSED") == nullptr;
+    if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, Q, 0);
+    if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
+    cudaFree(work);
+    if (rc != 0) return rc;
+    LMC_CHECK(e);
+    op->B_host.assign(B_host, B_host + (size_t)Q * D * D);
+    op->ranks.clear();
+    op->A_host.clear();
+    op->kappa_host.clear();
+    op->Q = Q;
+    return 0;
+}
+
+}  // namespace lmc
+
 extern "C" {
 
 int lmc_version(void) { return 100; }
@@ -29,6 +69,7 @@ int lmc_op_create(lmc_op** out, int D, int ndim, const int* grid_sizes, const do
     lmc_op* op = new lmc_op();
     op->D = D;
     op->ndim = ndim;
+    for (int p = 0; p < ndim; ++p) { op->origin[p] = origin[p]; op->delta[p] = delta[p]; }
     int rc = embedding_init(&op->emb, ndim, grid_sizes);
     if (rc == 0) rc = op->eng.init(op->emb);
     if (rc == 0) rc = build_points(&op->ps, D, ndim, grid_sizes, origin, delta, lens, X_host, op->emb.grid_pitch);
@@ -46,41 +87,16 @@ int lmc_op_set_params(lmc_op* op, int Q, const double* tops_host, const double* 
                       const double* noise_host) {
     LMC_REQUIRE(op && tops_host && B_host && noise_host, "null argument");
     LMC_REQUIRE(Q >= 1 && Q <= 64, "Q must be in 1..64");
-    const long bins = op->emb.bins, cells = op->emb.cells;
-    const int D = op->D;
-    if (Q > op->spec_cap) {
-        cudaFree(op->spec); cudaFree(op->B); cudaFree(op->specL);
-        op->spec = nullptr; op->B = nullptr; op->specL = nullptr; op->spec_cap = 0;
-        LMC_CHECK(cudaMalloc(&op->spec, sizeof(double) * (size_t)Q * bins));
-        LMC_CHECK(cudaMalloc(&op->specL, sizeof(double) * (size_t)Q * bins));
-        LMC_CHECK(cudaMalloc(&op->B, sizeof(double) * (size_t)Q * D * D));
-        op->spec_cap = Q;
-    }
-    if (!op->noise) LMC_CHECK(cudaMalloc(&op->noise, sizeof(double) * D));
+    const long cells = op->emb.cells;
     double* top_dev = nullptr;
-    cplx* work = nullptr;
     LMC_CHECK(cudaMalloc(&top_dev, sizeof(double) * (size_t)Q * cells));
-    cudaError_t e = cudaMalloc(&work, sizeof(cplx) * (size_t)bins);
-    if (e != cudaSuccess) { cudaFree(top_dev); LMC_CHECK(e); }
+    cudaError_t e = cudaMemcpy(top_dev, tops_host, sizeof(double) * (size_t)Q * cells, cudaMemcpyHostToDevice);
     int rc = 0;
-    e = cudaMemcpy(top_dev, tops_host, sizeof(double) * (size_t)Q * cells, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(op->B, B_host, sizeof(double) * (size_t)Q * D * D, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(op->noise, noise_host, sizeof(double) * D, cudaMemcpyHostToDevice);
-    for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q)
-        rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
-    op->fused = op->eng.fused_supported(D, Q) && getenv("LMC_NO_FUSED") == nullptr;
-    if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, Q, 0);
-    if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) rc = op_set_params_dev(op, Q, top_dev, B_host, noise_host);
     cudaFree(top_dev);
-    cudaFree(work);
-    if (rc != 0) return rc;
     LMC_CHECK(e);
-    op->B_host.assign(B_host, B_host + (size_t)Q * D * D);
-    op->ranks.clear();
-    op->A_host.clear();
-    op->kappa_host.clear();
-    op->Q = Q;
-    return 0;
+    if (rc == 0) { op->kinds.clear(); op->kparams.clear(); }   // tops came from the host: no kernel descriptors
+    return rc;
 }
 
 int lmc_op_set_coreg_factors(lmc_op* op, const int* ranks_host, const double* A_host,
@@ -288,7 +304,7 @@ int lmc_grad_grams(lmc_op* op, const double* alpha_dev, const double* R_dev, con
     LMC_REQUIRE(op && alpha_dev && quad_host && trace_host && nquad_host && ntrace_host, "null argument");
     LMC_REQUIRE(N == 0 || (R_dev && RINV_dev), "null probe blocks");
     LMC_REQUIRE(ntops_extra == 0 || tops_extra_host, "null derivative tops");
-    return grad_grams(op, alpha_dev, R_dev, RINV_dev, ld, N, ntops_extra, tops_extra_host, quad_host,
+    return grad_grams(op, alpha_dev, R_dev, RINV_dev, ld, N, ntops_extra, tops_extra_host, false, quad_host,
                       trace_host, nquad_host, ntrace_host, (cudaStream_t)stream);
 }
 

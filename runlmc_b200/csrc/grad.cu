@@ -150,7 +150,7 @@ static int cross_spectrum(int D, const cplx* U, const cplx* Z, long bins, int np
 }
 
 int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* RINV, long ld, int N,
-               int ntops_extra, const double* tops_extra_host, double* quad, double* trace,
+               int ntops_extra, const double* tops_extra, bool extra_on_device, double* quad, double* trace,
                double* nquad, double* ntrace, cudaStream_t st) {
     LMC_REQUIRE(op->Q > 0, "operator parameters not set");
     LMC_REQUIRE(N >= 0 && ntops_extra >= 0, "negative count");
@@ -166,12 +166,16 @@ int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* R
     double* spec = specb.as<double>();
     LMC_CHECK(cudaMemcpyAsync(spec, op->spec, sizeof(double) * (size_t)Q * bins, cudaMemcpyDeviceToDevice, st));
     if (ntops_extra) {
-        LMC_TRY(topb.alloc(sizeof(double) * (size_t)ntops_extra * cells));
         LMC_TRY(workb.alloc(sizeof(cplx) * (size_t)bins));
-        LMC_CHECK(cudaMemcpyAsync(topb.p, tops_extra_host, sizeof(double) * (size_t)ntops_extra * cells,
-                                  cudaMemcpyHostToDevice, st));
+        const double* tops_dev = tops_extra;   // derivative tops evaluated on the device (setup.cu) ...
+        if (!extra_on_device) {                // ... or uploaded by the caller
+            LMC_TRY(topb.alloc(sizeof(double) * (size_t)ntops_extra * cells));
+            LMC_CHECK(cudaMemcpyAsync(topb.p, tops_extra, sizeof(double) * (size_t)ntops_extra * cells,
+                                      cudaMemcpyHostToDevice, st));
+            tops_dev = topb.as<double>();
+        }
         for (int t = 0; t < ntops_extra; ++t)
-            LMC_TRY(op->eng.spectrum(topb.as<double>() + (size_t)t * cells, spec + (size_t)(Q + t) * bins,
+            LMC_TRY(op->eng.spectrum(tops_dev + (size_t)t * cells, spec + (size_t)(Q + t) * bins,
                                      workb.as<cplx>(), st));
     }
 

@@ -23,6 +23,45 @@ namespace lmc {
 // ---------------------------------------------------------------------------
 // host: sort points by bin
 // ---------------------------------------------------------------------------
+// Largest populations of the point windows the tiled 2-D kernels stage in shared memory, from the bin
+// CSR `start` ([D*NB + 1]); they pick the kernel variants at launch time.
+void tile_populations(PointSet* ps, const std::vector<int>& start) {
+    if (ps->ndim != 2) return;
+    const int D = ps->D;
+    // population of every (TX+3) x (TY+3) bin window the tiled scatter kernels stage in shared memory
+    auto worst_window = [&](int TX, int TY) {
+        const int BX = TX + 3, BY = TY + 3;
+        long worst = 0;
+        for (int d = 0; d < D; ++d)
+            for (int cx0 = 0; cx0 < ps->m[0]; cx0 += TX)
+                for (int cy0 = 0; cy0 < ps->m[1]; cy0 += TY) {
+                    long cnt = 0;
+                    for (int bx = cx0; bx < cx0 + BX && bx < ps->nb[0]; ++bx) {
+                        const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
+                        const int hi = std::min(cy0 + BY, ps->nb[1]);
+                        cnt += start[base + hi] - start[base + cy0];
+                    }
+                    worst = std::max(worst, cnt);
+                }
+        return (int)worst;
+    };
+    ps->max_tile_pts_8x8 = worst_window(8, 8);
+    ps->max_tile_pts_16x8 = worst_window(16, 8);
+    // population of every 16 x 16 tile of bins (no halo) the tiled gather kernel hands to one CTA
+    long worst = 0;
+    for (int d = 0; d < D; ++d)
+        for (int bx0 = 0; bx0 < ps->nb[0]; bx0 += 16)
+            for (int by0 = 0; by0 < ps->nb[1]; by0 += 16) {
+                long cnt = 0;
+                for (int bx = bx0; bx < bx0 + 16 && bx < ps->nb[0]; ++bx) {
+                    const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
+                    cnt += start[base + std::min(by0 + 16, ps->nb[1])] - start[base + by0];
+                }
+                worst = std::max(worst, cnt);
+            }
+    ps->max_gather_tile_pts = (int)worst;
+}
+
 int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const double* origin,
                  const double* delta, const int* lens, const double* X, long grid_pitch) {
     LMC_REQUIRE(D >= 1 && D <= 16, "number of outputs D must be in 1..16");
@@ -82,40 +121,7 @@ int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const dou
     bool ident = true;
     for (long g = 0; g < n; ++g) ident = ident && perm[g] == (int)g;
     ps->identity = ident;
-    if (ndim == 2) {
-        // population of every (TX+3) x (TY+3) bin window the tiled scatter kernels stage in shared memory
-        auto worst_window = [&](int TX, int TY) {
-            const int BX = TX + 3, BY = TY + 3;
-            long worst = 0;
-            for (int d = 0; d < D; ++d)
-                for (int cx0 = 0; cx0 < ps->m[0]; cx0 += TX)
-                    for (int cy0 = 0; cy0 < ps->m[1]; cy0 += TY) {
-                        long cnt = 0;
-                        for (int bx = cx0; bx < cx0 + BX && bx < ps->nb[0]; ++bx) {
-                            const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
-                            const int hi = std::min(cy0 + BY, ps->nb[1]);
-                            cnt += start[base + hi] - start[base + cy0];
-                        }
-                        worst = std::max(worst, cnt);
-                    }
-            return (int)worst;
-        };
-        ps->max_tile_pts_8x8 = worst_window(8, 8);
-        ps->max_tile_pts_16x8 = worst_window(16, 8);
-        // population of every 16 x 16 tile of bins (no halo) the tiled gather kernel hands to one CTA
-        long worst = 0;
-        for (int d = 0; d < D; ++d)
-            for (int bx0 = 0; bx0 < ps->nb[0]; bx0 += 16)
-                for (int by0 = 0; by0 < ps->nb[1]; by0 += 16) {
-                    long cnt = 0;
-                    for (int bx = bx0; bx < bx0 + 16 && bx < ps->nb[0]; ++bx) {
-                        const long base = (long)d * ps->NB + (long)bx * ps->nb[1];
-                        cnt += start[base + std::min(by0 + 16, ps->nb[1])] - start[base + by0];
-                    }
-                    worst = std::max(worst, cnt);
-                }
-        ps->max_gather_tile_pts = (int)worst;
-    }
+    tile_populations(ps, start);
     std::vector<int> si(n);
     std::vector<double> su(n);
     LMC_CHECK(cudaMalloc(&ps->perm, sizeof(int) * n));

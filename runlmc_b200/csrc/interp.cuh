@@ -1,6 +1,7 @@
 // Cubic-convolution interpolation between scattered points and the inducing grid.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace lmc {
 
@@ -30,6 +31,12 @@ struct PointSet {
 // u=f-i0 of reference approx/interpolation.py:98-101 bit for bit.
 int build_points(PointSet* ps, int D, int ndim, const int* grid_sizes, const double* origin,
                  const double* delta, const int* lens, const double* X_host, long grid_pitch);
+// Same point set from coordinates already on the device: keys, a stable radix sort and the bin CSR
+// are computed there (setup.cu); identical result, bit for bit.
+int build_points_dev(PointSet* ps, int D, int ndim, const int* grid_sizes, const double* origin,
+                     const double* delta, const int* lens, const double* X_dev, long grid_pitch,
+                     cudaStream_t st);
+void tile_populations(PointSet* ps, const std::vector<int>& start);
 void free_points(PointSet* ps);
 
 struct ColumnView {

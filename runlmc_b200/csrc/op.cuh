@@ -12,7 +12,12 @@ struct lmc_op {
     lmc::PointSet ps;
     double* spec = nullptr;   // [Q][bins] real circulant spectra / bins (digit-reversed layout)
     double* specL = nullptr;  // [Q][line][pos] line-major copy for the fused spectral kernel
+    double origin[2] = {0.0, 0.0}, delta[2] = {1.0, 1.0};   // grid axes: origin + k * delta
     std::vector<double> B_host;
+    // kernel descriptors of the last lmc_op_set_kernels (empty after lmc_op_set_params): kinds[Q],
+    // kparams[Q][2] = (inv_lengthscale, period)
+    std::vector<int> kinds;
+    std::vector<double> kparams;
     std::vector<int> ranks;          // optional factors B_q = A_q^T A_q + diag(kappa_q)
     std::vector<double> A_host, kappa_host;
     lmc::MixSpec mix_spec() const {
@@ -66,8 +71,10 @@ int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, co
 int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
                  int check_every, int* iters, double* resid, int* istop, cudaStream_t st);
 
+// tops_extra: [ntops_extra][cells] derivative tops, host memory unless extra_on_device
 int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* RINV, long ld, int N,
-               int ntops_extra, const double* tops_extra_host, double* quad, double* trace,
+               int ntops_extra, const double* tops_extra, bool extra_on_device, double* quad, double* trace,
                double* nquad, double* ntrace, cudaStream_t st);
+int op_set_params_dev(lmc_op* op, int Q, const double* top_dev, const double* B_host, const double* noise_host);
 
 }  // namespace lmc

@@ -15,12 +15,28 @@ def _dev(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+KERNEL_KINDS = {'RBF': 0, 'Matern32': 1, 'StdPeriodic': 2}   # LMC_KERN_* of include/lmc_b200.h
+
+
+def kernel_descriptor(k):
+    """(kind, inv_lengthscale, period) of a runlmc_b200.kern kernel the device can evaluate, or
+    None (then its values are computed on the host and uploaded)."""
+    from . import kern as _kern
+    for cls in (_kern.RBF, _kern.Matern32, _kern.StdPeriodic):
+        if type(k) is cls:
+            return KERNEL_KINDS[cls.__name__], float(k.inv_lengthscale), float(getattr(k, 'period', 1.0))
+    return None
+
+
 class FusedLMC:
     """:param Xs: list of D arrays of input points, each [n_d] or [n_d, ndim]
     :param grids: list of ndim equispaced 1-D grids (ndim in {1, 2})
+    :param build: 'device' (default): coordinates are uploaded once and the point sort runs on the
+        GPU (lmc_op_create_dev); 'host': the host counting sort (lmc_op_create).  Same operator,
+        bit for bit.
     """
 
-    def __init__(self, Xs, grids):
+    def __init__(self, Xs, grids, build='device'):
         self._h = ctypes.c_void_p()
         nat.require_cuda()
         grids = [np.asarray(g, dtype=np.float64) for g in grids]
@@ -45,10 +61,22 @@ class FusedLMC:
         delta = nat.as_f64([g[1] - g[0] for g in grids])   # interpolation.py:98
         lens = nat.as_i32(self.lens)
         X = nat.as_f64(np.vstack(Xs)) if self.n else np.zeros((0, ndim))
-        nat.check(nat.lib.lmc_op_create(
-            ctypes.byref(self._h), self.D, ndim, nat.host_ptr(sizes),
-            nat.host_ptr(origin), nat.host_ptr(delta), nat.host_ptr(lens),
-            nat.host_ptr(X)))
+        if build == 'device' and self.n:
+            torch = nat.require_cuda()
+            Xd = torch.as_tensor(X, device='cuda')
+            nat.check(nat.lib.lmc_op_create_dev(
+                ctypes.byref(self._h), self.D, ndim, nat.host_ptr(sizes),
+                nat.host_ptr(origin), nat.host_ptr(delta), nat.host_ptr(lens),
+                _dev(Xd), nat.current_stream_ptr()))
+        elif build in ('host', 'device'):
+            nat.check(nat.lib.lmc_op_create(
+                ctypes.byref(self._h), self.D, ndim, nat.host_ptr(sizes),
+                nat.host_ptr(origin), nat.host_ptr(delta), nat.host_ptr(lens),
+                nat.host_ptr(X)))
+        else:
+            raise ValueError('build should be "device" or "host"')
+        self.grid_deltas = [float(d) for d in delta]
+        self.kernels_on_device = False
         self.Q = 0
         self.shape = (self.n, self.n)
         self.dtype = np.float64
@@ -82,6 +110,46 @@ class FusedLMC:
         nat.check(nat.lib.lmc_op_set_params(
             self._h, Q, nat.host_ptr(tops), nat.host_ptr(Bs), nat.host_ptr(noise)))
         self.Q = Q
+        self.kernels_on_device = False
+        self._set_factors(Q, coreg_vecs, coreg_diags)
+
+    def set_kernels(self, kerns, Bs, noise, coreg_vecs=None, coreg_diags=None):
+        """Same update with the kernel values evaluated on the device (lmc_op_set_kernels): kerns
+        are Q runlmc_b200.kern RBF / Matern32 / StdPeriodic objects; their values on the operator's
+        own grid distances never exist on the host."""
+        desc = [kernel_descriptor(k) for k in kerns]
+        if any(d is None for d in desc):
+            raise ValueError('only RBF, Matern32 and StdPeriodic kernels are evaluated on the device')
+        kinds = nat.as_i32([d[0] for d in desc])
+        params = nat.as_f64([[d[1], d[2]] for d in desc])
+        Bs = nat.as_f64(np.array(Bs))
+        noise = nat.as_f64(noise)
+        Q = len(desc)
+        if Bs.shape != (Q, self.D, self.D):
+            raise ValueError('B shape {} != {}'.format(Bs.shape, (Q, self.D, self.D)))
+        if noise.shape != (self.D,):
+            raise ValueError('noise shape {} != {}'.format(noise.shape, (self.D,)))
+        nat.check(nat.lib.lmc_op_set_kernels(
+            self._h, Q, nat.host_ptr(kinds), nat.host_ptr(params), nat.host_ptr(Bs), nat.host_ptr(noise)))
+        self.Q = Q
+        self.kernels_on_device = True
+        self._set_factors(Q, coreg_vecs, coreg_diags)
+
+    def kernel_tops(self, deriv=False):
+        """The tops the device evaluated for set_kernels, [Q, m] (or [sum p_q, m] derivatives)."""
+        cnt = nat.lib.lmc_op_num_kernel_tops(self._h, int(deriv))
+        out = np.empty((cnt, self.m))
+        nat.check(nat.lib.lmc_op_kernel_tops(self._h, int(deriv), nat.host_ptr(out)))
+        return out
+
+    def grid_dists(self):
+        """||z - z_0|| of the operator's grid, as the device evaluates it (interpolated_llgp.py:431)."""
+        ax = [np.arange(m) * d for m, d in zip(self.grid_sizes, self.grid_deltas)]
+        if self.ndim == 1:
+            return ax[0]
+        return np.sqrt(ax[0][:, None] ** 2 + ax[1][None, :] ** 2)
+
+    def _set_factors(self, Q, coreg_vecs, coreg_diags):
         if coreg_vecs is not None and coreg_diags is not None:
             vecs = [np.atleast_2d(np.asarray(a, dtype=np.float64)) for a in coreg_vecs]
             ranks = nat.as_i32([len(a) for a in vecs])
@@ -204,12 +272,19 @@ class FusedLMC:
 
     # ---- gradient contractions --------------------------------------------
     def grad_grams_device(self, alpha, R, RINV, extra_tops=()):
-        """alpha [n], R/RINV [N, n] CUDA tensors; extra_tops: derivative tops.
-        Returns (quad[T,D,D], trace[T,D,D], nquad[D], ntrace[D]) numpy, T = Q + len(extra_tops)."""
+        """alpha [n], R/RINV [N, n] CUDA tensors; extra_tops: derivative tops, or None for the
+        derivative tops of the kernels given to set_kernels (evaluated on the device).
+        Returns (quad[T,D,D], trace[T,D,D], nquad[D], ntrace[D]) numpy, T = Q + number of extra tops."""
         torch = nat.require_cuda()
         N = 0 if R is None else R.shape[0]
-        ext = nat.as_f64(np.array([np.asarray(t, dtype=np.float64).ravel() for t in extra_tops])
-                         if len(extra_tops) else np.zeros((0, self.m)))
+        on_device = extra_tops is None
+        if on_device:
+            if not self.kernels_on_device:
+                raise ValueError('derivative tops on the device need set_kernels')
+            ext = np.zeros((nat.lib.lmc_op_num_kernel_tops(self._h, 1), 0))
+        else:
+            ext = nat.as_f64(np.array([np.asarray(t, dtype=np.float64).ravel() for t in extra_tops])
+                             if len(extra_tops) else np.zeros((0, self.m)))
         T = self.Q + ext.shape[0]
         D = self.D
         quad = np.zeros((T, D, D))
@@ -219,6 +294,12 @@ class FusedLMC:
         assert alpha.is_contiguous() and alpha.dtype == torch.float64
         if N:
             assert R.is_contiguous() and RINV.is_contiguous() and R.shape == RINV.shape
+        if on_device:
+            nat.check(nat.lib.lmc_grad_grams_kernels(
+                self._h, _dev(alpha), _dev(R) if N else None, _dev(RINV) if N else None, self.n, N,
+                nat.host_ptr(quad), nat.host_ptr(trace), nat.host_ptr(nquad), nat.host_ptr(ntrace),
+                nat.current_stream_ptr()))
+            return quad, trace, nquad, ntrace
         nat.check(nat.lib.lmc_grad_grams(
             self._h, _dev(alpha), _dev(R) if N else None, _dev(RINV) if N else None,
             self.n, N, ext.shape[0], nat.host_ptr(ext) if ext.shape[0] else None,

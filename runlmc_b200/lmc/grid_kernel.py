@@ -20,7 +20,7 @@ from ..linalg.identity import Identity
 from ..linalg.kronecker import Kronecker
 from ..linalg.numpy_matrix import NumpyMatrix
 from ..linalg.sum_matrix import SumMatrix
-from ..fused import FusedLMC
+from ..fused import FusedLMC, kernel_descriptor
 
 
 class GridKernel(Matrix):
@@ -98,12 +98,33 @@ def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
     if cache is None:
         cache = FusedLMC(Xs, grids)          # X-dependent sort happens once per model
         W._lmc_fused = cache
-    grid_k = fk.eval_kernels_fixed_dim(grid_dists[active_dim], active_dim)
     idxs = fk.active_dims[active_dim]
-    cache.set_params(list(grid_k), fk.coreg_mats(active_dim), fk.noise,
-                     coreg_vecs=[fk.coreg_vecs[i] for i in idxs],
-                     coreg_diags=[fk.coreg_diags[i] for i in idxs])
+    factors = dict(coreg_vecs=[fk.coreg_vecs[i] for i in idxs],
+                   coreg_diags=[fk.coreg_diags[i] for i in idxs])
+    kerns = _device_kernels(fk, idxs, cache, grid_dists[active_dim])
+    if kerns is not None:
+        # per-step setup on the device: kernel values are evaluated where the spectra are computed
+        cache.set_kernels(kerns, fk.coreg_mats(active_dim), fk.noise, **factors)
+    else:
+        grid_k = fk.eval_kernels_fixed_dim(grid_dists[active_dim], active_dim)
+        cache.set_params(list(grid_k), fk.coreg_mats(active_dim), fk.noise, **factors)
     return cache
+
+
+def _device_kernels(fk, idxs, fused, dists):
+    """The kernels of this group if the device can evaluate all of them on its own grid distances
+    (they must be the distances the caller passed), else None."""
+    kernels = getattr(fk, '_kernels', None)
+    if kernels is None:
+        return None
+    kerns = [kernels[i] for i in idxs]
+    if any(kernel_descriptor(k) is None for k in kerns):
+        return None
+    own = fused.grid_dists()
+    dists = np.asarray(dists)
+    if dists.shape != own.shape or not np.allclose(dists, own, rtol=1e-13, atol=1e-13 * max(1.0, float(own.max()))):
+        return None
+    return kerns
 
 
 def _gen_slfm_grid(fk, grid_k, m, active_dim):

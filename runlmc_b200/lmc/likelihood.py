@@ -83,19 +83,28 @@ class ApproxLMCLikelihood(LMCLikelihood):
     def __init__(self, functional_kernel, grid_kern, grid_dists, interpolants, Ys, deriv):
         super().__init__(functional_kernel, Ys)
         self.grid_dists = grid_dists
-        self._kernels_on_grid = self.functional_kernel.eval_kernels(grid_dists)
         self._materialized = None
+        self._materialized_grads = None
         self.K = grid_kern
         self.deriv = deriv.generate(self.K, self.y)
-        self.materialized_grads = self.functional_kernel.eval_kernel_gradients(grid_dists)
         self.interpolants = interpolants
         self._fused_grads = None
 
+    # The reference evaluates both on construction (likelihood.py:103-108); here they are evaluated
+    # on first use, because with device-evaluated kernels (lmc_op_set_kernels) the fused gradient
+    # path never needs them on the host.
     @property
     def materialized_kernels(self):
         if self._materialized is None:
-            self._materialized = [BTTB(d.ravel(), d.shape) for d in self._kernels_on_grid]
+            self._materialized = [BTTB(d.ravel(), d.shape)
+                                  for d in self.functional_kernel.eval_kernels(self.grid_dists)]
         return self._materialized
+
+    @property
+    def materialized_grads(self):
+        if self._materialized_grads is None:
+            self._materialized_grads = self.functional_kernel.eval_kernel_gradients(self.grid_dists)
+        return self._materialized_grads
 
     # -- fused path -------------------------------------------------------
     def _fused(self):
@@ -104,13 +113,17 @@ class ApproxLMCLikelihood(LMCLikelihood):
             return None
         if self._fused_grads is None:
             fk = self.functional_kernel
-            extra = [t for ts in self.materialized_grads for t in ts]
             d = self.deriv
+            if fused.kernels_on_device:
+                extra = None          # derivative tops are evaluated on the device too
+                counts = [len(k.param_values()) for k in fk._kernels]
+            else:
+                extra = [t for ts in self.materialized_grads for t in ts]
+                counts = [len(t) for t in self.materialized_grads]
             quad, trace, nquad, ntrace = fused.grad_grams(
                 d.alpha, np.asarray(d._rs, dtype=np.float64), np.asarray(d._inv_rs), extra)
             self._fused_grads = assemble_gradients(
-                fk.coreg_vecs, fk.coreg_mats(), [len(t) for t in self.materialized_grads],
-                d._n_it, quad, trace, nquad, ntrace)
+                fk.coreg_vecs, fk.coreg_mats(), counts, d._n_it, quad, trace, nquad, ntrace)
         return self._fused_grads
 
     def coreg_vec_gradients(self):
