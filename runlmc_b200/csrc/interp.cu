@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
                     const double* pv = vre + ibeg * VP;
                     const unsigned char* pby = s.by + ibeg;
                     const unsigned char* pby_end = s.by + iend;
-#pragma unroll 1
+#pragma unroll 2   // two points in flight: their shared-memory loads overlap (1.43 -> 1.41 ms at config E)
                     for (; pby < pby_end; ++pby, ++pw, ++pwy, pv += VP) {
                         const double wyv = pwy[-(int)pby[0] * CAP];
                         const double t0 = wyv * pv[0], t1 = wyv * pv[CAP * VP];
