@@ -237,8 +237,10 @@ def run_own(args):
     from runlmc_b200.fused import FusedLMC
     from runlmc_b200.distributed import shard_bounds, sharded_gradient
     dev = torch.device('cuda', local)
-    op = FusedLMC(prob.Xs, prob.grids)
-    op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+    from runlmc_b200.kern import RBF
+    op = FusedLMC(prob.Xs, prob.grids)                       # point sort on the device
+    op.set_kernels([RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
+                   prob.coreg_diags)                         # kernel values evaluated on the device
     lo, hi = shard_bounds(prob.N, rank, world)
     rows = [prob.y[None, :]] if rank == 0 else []
     rows.append(prob.probes[lo:hi])
@@ -339,7 +341,7 @@ def run_own(args):
     if not args.no_grad:
         barrier()
         t0 = time.perf_counter()
-        grads, stats = sharded_gradient(op, prob.y, prob.probes, prob.top_grads, prob.coreg_vecs,
+        grads, stats = sharded_gradient(op, prob.y, prob.probes, None, prob.coreg_vecs,
                                         prob.coreg_mats(), tol=1e-4, rank=rank, world=world)
         barrier()
         dt = time.perf_counter() - t0

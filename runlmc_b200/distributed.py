@@ -45,6 +45,9 @@ def sharded_gradient(fused, y, probes, kernel_grad_tops, coreg_vecs, coreg_mats,
     ranks.  `probes` is the full [N, n] block (identical on every rank, e.g.
     from a shared seed); each rank touches only its slice.
 
+    `kernel_grad_tops`: per kernel, the list of its derivative tops dk_q/dtheta on the grid -- or None
+    when the operator evaluates its kernels on the device (FusedLMC.set_kernels).
+
     Returns (grads, stats): grads = (coreg_vec, coreg_diag, kernel, noise) as
     in ApproxLMCLikelihood, stats = dict(iterations, solv_error) (means over
     all N+1 solves, like Metrics, stochastic_deriv.py:42-45)."""
@@ -60,14 +63,16 @@ def sharded_gradient(fused, y, probes, kernel_grad_tops, coreg_vecs, coreg_mats,
     if len(local):
         RHS[1:].copy_(torch.as_tensor(np.ascontiguousarray(local)))
     X, iters, resid, _ = fused.minres_device(RHS, tol=tol)
-    extra = [t for ts in kernel_grad_tops for t in ts]
+    if kernel_grad_tops is None:      # derivative tops of the kernels given to set_kernels, on the device
+        extra, counts = None, fused.kernel_param_counts
+    else:
+        extra, counts = [t for ts in kernel_grad_tops for t in ts], [len(t) for t in kernel_grad_tops]
     quad, trace, nquad, ntrace = fused.grad_grams_device(
         X[0], RHS[1:] if len(local) else None, X[1:] if len(local) else None, extra)
     alpha = X[0].cpu().numpy()
     it_sum = float(np.sum(iters[1:])) + (float(iters[0]) if rank == 0 else 0.0)
     rs_sum = float(np.sum(resid[1:])) + (float(resid[0]) if rank == 0 else 0.0)
     trace, ntrace, it_sum, rs_sum = allreduce_trace(trace, ntrace, it_sum, rs_sum, group)
-    grads = assemble_gradients(coreg_vecs, coreg_mats, [len(t) for t in kernel_grad_tops], N,
-                               quad, trace, nquad, ntrace)
+    grads = assemble_gradients(coreg_vecs, coreg_mats, counts, N, quad, trace, nquad, ntrace)
     stats = {'iterations': it_sum / (N + 1), 'solv_error': rs_sum / (N + 1), 'alpha': alpha}
     return grads, stats

@@ -133,6 +133,7 @@ class FusedLMC:
             self._h, Q, nat.host_ptr(kinds), nat.host_ptr(params), nat.host_ptr(Bs), nat.host_ptr(noise)))
         self.Q = Q
         self.kernels_on_device = True
+        self.kernel_param_counts = [2 if d[0] == KERNEL_KINDS['StdPeriodic'] else 1 for d in desc]
         self._set_factors(Q, coreg_vecs, coreg_diags)
 
     def kernel_tops(self, deriv=False):

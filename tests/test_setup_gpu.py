@@ -171,3 +171,23 @@ def test_gen_grid_kernel_uses_device_kernels_only_on_matching_distances():
     K2, _ = gen_grid_kernel(fk, warped, interps, prob.lens)
     assert not fused_of(K2).kernels_on_device
     assert rel_err(K2.matvec(g['V'][0]), g['KV'][0]) > 1e-6     # really the warped kernel
+
+
+def test_sharded_gradient_with_device_kernels():
+    """A whole gradient evaluation with device-evaluated kernels and derivative tops (what bench.py
+    times) against the same evaluation with uploaded tops."""
+    from test_oracle_golden import GOLDEN_PROBLEMS
+    from runlmc_b200 import kern
+    from runlmc_b200.fused import FusedLMC
+    from runlmc_b200.distributed import sharded_gradient
+    prob = GOLDEN_PROBLEMS['lmc_2d']()
+    op_u = FusedLMC(prob.Xs, prob.grids, build='host')
+    op_u.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+    op_k = FusedLMC(prob.Xs, prob.grids)
+    op_k.set_kernels([kern.RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
+                     prob.coreg_diags)
+    gu, su = sharded_gradient(op_u, prob.y, prob.probes, prob.top_grads, prob.coreg_vecs, prob.coreg_mats())
+    gk, sk = sharded_gradient(op_k, prob.y, prob.probes, None, prob.coreg_vecs, prob.coreg_mats())
+    assert rel_err(sk['alpha'], su['alpha']) < 1e-6            # tops differ by ulps; MINRES amplifies
+    for a, b in zip(gk, gu):
+        assert rel_err(np.array(a, dtype=float), np.array(b, dtype=float)) < 1e-5
