@@ -128,6 +128,19 @@ int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* 
                     double tol, int maxiter, int check_every, int* iters_host,
                     double* resid_host, int* istop_host);
 
+/* ---- batched conjugate gradients ---------------------------------------------
+ * Iterative.solve(..., minres=False) (iterative.py:44-51): scipy.sparse.linalg.cg with M = I, x0 = 0,
+ * rtol = min(1e-10, tol), atol = 0, maxiter, behind the same true-residual test every `check_every`-th
+ * iteration.  iters/resid as for lmc_minres; info[P] <- scipy's info (0 converged, maxiter if the
+ * iterations ran out), or 10 if stopped by the residual test.                                      */
+int lmc_cg(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol, int maxiter,
+           int check_every, int* iters_host, double* resid_host, int* info_host, void* stream);
+int lmc_cg_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host, double tol, int maxiter,
+                int check_every, int* iters_host, double* resid_host, int* info_host);
+int lmc_cg_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratch_in_dev, double* scratch_out_dev,
+                   const double* RHS_dev, long ld, int P, double* X_dev, double tol, int maxiter,
+                   int check_every, int* iters_host, double* resid_host, int* info_host, void* stream);
+
 /* Same solver for an operator tree composed by the caller (the runlmc.linalg mirror
  * classes): for every product the solver writes the [P][n] input block to
  * scratch_in_dev, calls apply_cb(ctx) -- which must leave K * scratch_in in

@@ -570,14 +570,49 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=()):
     return x, istop, itn, trace
 
 
+def cg(matvec, b, rtol, maxiter, callback=None):
+    """scipy.sparse.linalg.cg (scipy 1.18.1 _isolve/iterative.py, the loop after
+    ``make_system``) with M = I, x0 = 0, atol = 0 -- the solver behind
+    Iterative.solve(..., minres=False) (iterative.py:44-51).
+    Returns (x, info, iterations)."""
+    b = np.asarray(b, dtype=float)
+    bnrm2 = np.linalg.norm(b)
+    atol = max(0.0, float(rtol) * float(bnrm2))
+    if bnrm2 == 0:
+        return b.copy(), 0, 0
+    x = np.zeros_like(b)
+    r = b.copy()
+    rho_prev, p = None, None
+    for iteration in range(maxiter):
+        if np.linalg.norm(r) < atol:
+            return x, 0, iteration
+        z = r                       # identity preconditioner
+        rho_cur = np.dot(r, z)
+        if iteration > 0:
+            beta = rho_cur / rho_prev
+            p *= beta
+            p += z
+        else:
+            p = z.copy()
+        q = matvec(p)
+        alpha = rho_cur / np.dot(p, q)
+        x += alpha * p
+        r -= alpha * q
+        rho_prev = rho_cur
+        if callback is not None:
+            callback(x)
+    return x, maxiter, maxiter
+
+
 class _Early(Exception):
     def __init__(self, x):
         super().__init__('')
         self.x = x
 
 
-def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100):
-    """Iterative.solve with verbose=True, minres=True; iterative.py:24-62.
+def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100, use_minres=True):
+    """Iterative.solve with verbose=True (minres=True unless ``use_minres`` is false: then scipy's cg
+    restated above runs behind the same wrapper); iterative.py:24-62.
 
     rtol = min(1e-10, tol), maxiter = n, and on every 100th callback the true
     residual ||y - Kx||_2 is formed; < tol terminates (iterative.py:36-42).
@@ -599,10 +634,12 @@ def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100):
         if use_scipy:
             op = scipy.sparse.linalg.LinearOperator(
                 (n, n), matvec=matvec, dtype=np.float64)
-            x, _ = scipy.sparse.linalg.minres(
-                op, y, rtol=rtol, maxiter=n, callback=cb)
-        else:
+            method = scipy.sparse.linalg.minres if use_minres else scipy.sparse.linalg.cg
+            x, _ = method(op, y, rtol=rtol, maxiter=n, callback=cb)
+        elif use_minres:
             x, _, _, _ = minres(matvec, y, rtol, n, callback=cb)
+        else:
+            x, _, _ = cg(matvec, y, rtol, n, callback=cb)
     except _Early as e:
         x = e.x
     err = np.linalg.norm(y - matvec(x))

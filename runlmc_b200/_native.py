@@ -63,6 +63,9 @@ SIGNATURES = {
     'lmc_minres': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
     'lmc_minres_host': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p]),
     'lmc_minres_generic': (_i, [_p, _p, _l, _p, _p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
+    'lmc_cg': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
+    'lmc_cg_host': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p]),
+    'lmc_cg_generic': (_i, [_p, _p, _l, _p, _p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
     'lmc_block_dot': (_i, [_p, _l, _p, _l, _l, _i, _p, _p]),
     'lmc_grad_grams': (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _p, _p]),
     'lmc_bttb_create': (_i, [ctypes.POINTER(_p), _i, _p, _p]),

@@ -17,14 +17,16 @@ def fused_of(K):
     return getattr(K, '_fused', None)
 
 
-def solve_block(K, RHS, tol=1e-4, maxiter=None, check_every=100):
-    """Batched solve of the rows of RHS.  Returns (X, iters, resid, istop)."""
+def solve_block(K, RHS, tol=1e-4, maxiter=None, check_every=100, minres=True):
+    """Batched solve of the rows of RHS with MINRES (or scipy's cg recurrence if not `minres`).
+    Returns (X, iters, resid, istop)."""
     RHS = nat.as_f64(RHS)
     if RHS.ndim == 1:
         RHS = RHS.reshape(1, -1)
     fused = fused_of(K)
     if fused is not None:
-        return fused.minres(RHS, tol=tol, maxiter=maxiter, check_every=check_every)
+        solver = fused.minres if minres else fused.cg
+        return solver(RHS, tol=tol, maxiter=maxiter, check_every=check_every)
     # arbitrary operator tree: same device MINRES, the product is a callback
     # into the tree's own device kernels
     torch = nat.require_cuda()
@@ -46,7 +48,8 @@ def solve_block(K, RHS, tol=1e-4, maxiter=None, check_every=100):
     iters = np.zeros(P, dtype=np.int32)
     resid = np.zeros(P, dtype=np.float64)
     istop = np.zeros(P, dtype=np.int32)
-    nat.check(nat.lib.lmc_minres_generic(
+    entry = nat.lib.lmc_minres_generic if minres else nat.lib.lmc_cg_generic
+    nat.check(entry(
         ctypes.cast(cb, ctypes.c_void_p), None, n, dev.ptr(s_in), dev.ptr(s_out), dev.ptr(rhs_d), n, P, dev.ptr(x_d), float(tol),
         int(n if maxiter is None else maxiter), int(check_every), nat.host_ptr(iters),
         nat.host_ptr(resid), nat.host_ptr(istop), dev.stream()))
@@ -58,18 +61,17 @@ class Iterative:
 
     @staticmethod
     def solve(K, y, verbose=False, minres=True, tol=1e-4):
-        """Solves K x = y with MINRES exactly as the reference wrapper does
-        (iterative.py:24-62): rtol = min(1e-10, tol), maxiter = n, true-residual
-        early termination every 100 iterations; never raises on
+        """Solves K x = y with MINRES (or, with minres=False, scipy's cg) exactly as the
+        reference wrapper does (iterative.py:24-62): rtol = min(1e-10, tol), maxiter = n,
+        true-residual early termination every 100 iterations; never raises on
         non-convergence, logs instead.
 
         :return: x, and (iterations, error) too if verbose"""
-        if not minres:
-            raise NotImplementedError('lcg (minres=False) is not part of the accelerated path')
         y = np.asarray(y, dtype=np.float64)
-        X, iters, resid, istop = solve_block(K, y.reshape(1, -1), tol=tol)
+        X, iters, resid, istop = solve_block(K, y.reshape(1, -1), tol=tol, minres=minres)
         n = K.shape[0]
-        if resid[0] > tol or istop[0] == 6:
+        exhausted = istop[0] == 6 if minres else istop[0] not in (0, 10)
+        if resid[0] > tol or exhausted:
             _LOG.critical('MINRES (n = %d) did not converge in n iterations.'
                           ' Reconstruction error %e', n, resid[0])
         if verbose:

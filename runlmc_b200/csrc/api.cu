@@ -298,6 +298,29 @@ int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* 
     return 0;
 }
 
+int lmc_cg(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol, int maxiter,
+           int check_every, int* iters_host, double* resid_host, int* info_host, void* stream) {
+    LMC_REQUIRE(op && RHS_dev && X_dev, "null argument");
+    return cg_solve(op, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host, info_host,
+                    (cudaStream_t)stream);
+}
+
+int lmc_cg_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host, double tol, int maxiter,
+                int check_every, int* iters_host, double* resid_host, int* info_host) {
+    LMC_REQUIRE(op && RHS_host && X_host, "null argument");
+    LMC_REQUIRE(P >= 1 && ld >= op->ps.n, "bad block shape");
+    HostBlock in, out;
+    const size_t bytes = sizeof(double) * (size_t)P * ld;
+    LMC_CHECK(cudaMalloc(&in.p, bytes));
+    LMC_CHECK(cudaMalloc(&out.p, bytes));
+    LMC_CHECK(cudaMemcpy(in.p, RHS_host, bytes, cudaMemcpyHostToDevice));
+    LMC_CHECK(cudaMemset(out.p, 0, bytes));
+    LMC_TRY(cg_solve(op, in.p, ld, P, out.p, tol, maxiter, check_every, iters_host, resid_host, info_host,
+                     nullptr));
+    LMC_CHECK(cudaMemcpy(X_host, out.p, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int lmc_grad_grams(lmc_op* op, const double* alpha_dev, const double* R_dev, const double* RINV_dev,
                    long ld, int N, int ntops_extra, const double* tops_extra_host, double* quad_host,
                    double* trace_host, double* nquad_host, double* ntrace_host, void* stream) {

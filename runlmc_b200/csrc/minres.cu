@@ -491,6 +491,242 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
     return minres_core(A, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st);
 }
 
+
+// ---------------------------------------------------------------------------
+// Batched conjugate gradients: Iterative.solve(..., minres=False) (iterative.py:44-51 ->
+// scipy.sparse.linalg.cg, scipy 1.18.1 _isolve/iterative.py) with M = I, x0 = 0, atol = 0,
+// rtol = min(1e-10, tol), maxiter (reference: n) and the wrapper's true-residual test every
+// `check_every` iterations.  Same layout and conventions as the MINRES block solver above.
+// ---------------------------------------------------------------------------
+struct CgState {
+    double atol, rho, rho_prev, beta, resid;
+    int itn, done, info;   // info: scipy's second return value (0 converged, maxiter if exhausted); 10 = residual test
+};
+
+// r = b_sorted, x = 0 ; partial ||b||^2
+__global__ void __launch_bounds__(kVecThreads) cg_init_kernel(const double* __restrict__ RHS, long ld,
+                                                              const int* __restrict__ perm, long n, double* b,
+                                                              double* r, double* x, double* part, int nblk) {
+    const int col = blockIdx.y;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const double v = RHS[(long)col * ld + (perm ? perm[i] : i)];
+            const long o = (long)col * n + i;
+            b[o] = v; r[o] = v; x[o] = 0.0;
+            acc = fma(v, v, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+__global__ void cg_init_scalars_kernel(CgState* st, int* active, const double* part, int nblk, int P, double rtol,
+                                       int* n_active) {
+    const int col = blockIdx.x;
+    const double s = column_sum(part + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    CgState c = {};
+    const double bnrm2 = sqrt(s);
+    c.atol = rtol * bnrm2;               // _get_atol_rtol with atol = 0
+    c.rho = s;                           // r = b, z = r
+    c.beta = 0.0;
+    c.done = (bnrm2 == 0.0 || bnrm2 < c.atol) ? 1 : 0;   // scipy returns b (= 0) at once
+    st[col] = c;
+    active[col] = c.done ? 0 : 1;
+    if (col == 0) *n_active = -1;
+}
+
+// p = beta p + r   (first iteration: beta = 0, p is not read)
+__global__ void __launch_bounds__(kVecThreads) cg_c1_kernel(double* p, const double* __restrict__ r, const CgState* st,
+                                                            const int* active, long n) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const double beta = st[col].beta;
+    const bool first = st[col].itn == 0;
+    const long base = (long)blockIdx.x * kVecChunk;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            p[o] = first ? r[o] : __dadd_rn(__dmul_rn(p[o], beta), r[o]);
+        }
+    }
+}
+
+// partial p . q
+__global__ void __launch_bounds__(kVecThreads) cg_c2_kernel(const double* __restrict__ p, const double* __restrict__ q,
+                                                            const int* active, long n, double* part, int nblk) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) acc = fma(p[(long)col * n + i], q[(long)col * n + i], acc);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// alpha = rho / (p . q) ; x += alpha p ; r -= alpha q ; partial r . r
+__global__ void __launch_bounds__(kVecThreads) cg_c3_kernel(double* x, double* r, const double* __restrict__ p,
+                                                            const double* __restrict__ q, const CgState* st,
+                                                            const int* active, long n, const double* part_pq,
+                                                            double* part_rr, int nblk) {
+    const int col = blockIdx.y;
+    if (!active[col]) return;
+    const double pq = block_sum_partials(part_pq + (long)col * nblk, nblk);
+    const double alpha = st[col].rho / pq;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) {
+            const long o = (long)col * n + i;
+            x[o] = __dadd_rn(x[o], __dmul_rn(alpha, p[o]));
+            const double rv = __dsub_rn(r[o], __dmul_rn(alpha, q[o]));
+            r[o] = rv;
+            acc = fma(rv, rv, acc);
+        }
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part_rr[(long)col * nblk + blockIdx.x] = acc;
+}
+
+// end of an iteration: rho bookkeeping, scipy's stopping test (top of its next iteration), beta
+__global__ void cg_scalars_kernel(CgState* st, int* active, const double* part_rr, int nblk, int P, int maxiter,
+                                  int* n_active) {
+    const int col = blockIdx.x;
+    if (col == 0 && threadIdx.x == 0) *n_active = 0;
+    if (!active[col]) return;
+    const double s = column_sum(part_rr + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    CgState c = st[col];
+    c.itn += 1;
+    c.rho_prev = c.rho;
+    c.rho = s;
+    c.beta = c.rho / c.rho_prev;
+    if (c.itn >= maxiter) { c.done = 1; c.info = maxiter; }
+    else if (sqrt(s) < c.atol) { c.done = 1; c.info = 0; }
+    if (c.done) active[col] = 0;
+    st[col] = c;
+}
+
+__global__ void cg_count_active_kernel(const int* active, int P, int* n_active) {
+    int cnt = 0;
+    for (int c = threadIdx.x; c < P; c += blockDim.x) cnt += active[c] != 0;
+    if (cnt) atomicAdd(n_active, cnt);
+}
+
+__global__ void cg_resid_scalars_kernel(CgState* st, int* active, const double* part, int nblk, int P, double tol,
+                                        int final_pass, int* n_active) {
+    const int col = blockIdx.x;
+    if (!final_pass && !active[col]) return;
+    const double s = column_sum(part + (long)col * nblk, nblk);
+    if (threadIdx.x != 0) return;
+    const double rn = sqrt(s);
+    st[col].resid = rn;
+    if (!final_pass) {
+        if (rn < tol) { st[col].info = 10; st[col].done = 1; active[col] = 0; }
+        else atomicAdd(n_active, 1);
+    }
+}
+
+static int cg_core(MinresOperator& A, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                   int check_every, int* iters, double* resid, int* info, cudaStream_t st) {
+    LMC_REQUIRE(P >= 1, "need at least one right-hand side");
+    LMC_REQUIRE(maxiter >= 1 && check_every >= 1, "maxiter/check_every must be positive");
+    const long n = A.n;
+    LMC_REQUIRE(ld >= n, "leading dimension < n");
+    const int nblk = ceil_div(n, kVecChunk);
+    const double rtol = std::fmin(1e-10, tol);
+    const size_t vec = sizeof(double) * (size_t)P * n;
+    const size_t vec_al = (vec + 255) & ~(size_t)255;
+    LMC_TRY(g_ws.reserve(vec_al * 5));
+    WsSlice bufs[5];
+    for (int i = 0; i < 5; ++i) bufs[i].p = static_cast<char*>(g_ws.p) + vec_al * i;
+    double *b = bufs[0].as<double>(), *x = bufs[1].as<double>(), *r = bufs[2].as<double>();
+    double *p = bufs[3].as<double>(), *q = bufs[4].as<double>();
+    DevBuf parts[2], stb, act, nact;
+    for (auto& pb : parts) LMC_TRY(pb.alloc(sizeof(double) * (size_t)P * nblk));
+    LMC_TRY(stb.alloc(sizeof(CgState) * P));
+    LMC_TRY(act.alloc(sizeof(int) * P));
+    LMC_TRY(nact.alloc(sizeof(int)));
+    double *pa = parts[0].as<double>(), *pr = parts[1].as<double>();
+    CgState* cs = stb.as<CgState>();
+    int* active = act.as<int>();
+    int* n_active = nact.as<int>();
+    const int* perm = A.perm;
+    const dim3 vgrid((unsigned)nblk, (unsigned)P);
+
+    cg_init_kernel<<<vgrid, kVecThreads, 0, st>>>(RHS, ld, perm, n, b, r, x, pa, nblk);
+    cg_init_scalars_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, rtol, n_active);
+    count_launch(2);
+    LMC_CHECK(cudaGetLastError());
+
+    int h_active = P;
+    const int poll = 8;
+    for (int itn = 1; itn <= maxiter; ++itn) {
+        {
+            ProfScope prof(PROF_MINRES_VEC, st);
+            cg_c1_kernel<<<vgrid, kVecThreads, 0, st>>>(p, r, cs, active, n);
+        }
+        LMC_TRY(A.apply(p, nullptr, active, q, P, st));
+        {
+            ProfScope prof(PROF_MINRES_VEC, st);
+            cg_c2_kernel<<<vgrid, kVecThreads, 0, st>>>(p, q, active, n, pa, nblk);
+            cg_c3_kernel<<<vgrid, kVecThreads, 0, st>>>(x, r, p, q, cs, active, n, pa, pr, nblk);
+        }
+        {
+            ProfScope prof(PROF_MINRES_SCALAR, st);
+            cg_scalars_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pr, nblk, P, maxiter, n_active);
+            cg_count_active_kernel<<<1, 128, 0, st>>>(active, P, n_active);
+        }
+        count_launch(5);
+        bool polled = false;
+        if (itn % check_every == 0) {
+            // reference callback: true residual of the columns still running (iterative.py:36-42)
+            LMC_TRY(A.apply(x, nullptr, active, q, P, st));
+            minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, q, active, n, pa, nblk);
+            LMC_CHECK(cudaMemsetAsync(n_active, 0, sizeof(int), st));
+            cg_resid_scalars_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
+            count_launch(2);
+            polled = true;
+        }
+        if (polled || itn % poll == 0 || itn == maxiter) {
+            LMC_CHECK(cudaMemcpyAsync(&h_active, n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LMC_CHECK(cudaStreamSynchronize(st));
+            if (h_active == 0) break;
+        }
+    }
+    // final residual of every column (iterative.py:53)
+    LMC_TRY(A.apply(x, nullptr, nullptr, q, P, st));
+    minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, q, nullptr, n, pa, nblk);
+    cg_resid_scalars_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
+    minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(x, perm, n, X, ld);
+    count_launch(3);
+    LMC_CHECK(cudaGetLastError());
+    std::vector<CgState> h((size_t)P);
+    LMC_CHECK(cudaMemcpyAsync(h.data(), cs, sizeof(CgState) * P, cudaMemcpyDeviceToHost, st));
+    LMC_CHECK(cudaStreamSynchronize(st));
+    for (int c = 0; c < P; ++c) {
+        if (iters) iters[c] = h[c].itn;
+        if (resid) resid[c] = h[c].resid;
+        if (info) info[c] = h[c].info;
+    }
+    return 0;
+}
+
+int cg_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+             int check_every, int* iters, double* resid, int* info, cudaStream_t st) {
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+    FusedOperator A(op);
+    return cg_core(A, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, info, st);
+}
+
 // sum over a [ncols][n] block of A .* B, two-stage deterministic
 __global__ void __launch_bounds__(kVecThreads) block_dot_kernel(const double* __restrict__ A,
                                                                const double* __restrict__ B, long lda,
@@ -523,6 +759,18 @@ int lmc_minres_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratc
     A.scratch_in = scratch_in_dev; A.scratch_out = scratch_out_dev;
     return minres_core(A, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
                        istop_host, (cudaStream_t)stream);
+}
+
+int lmc_cg_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratch_in_dev, double* scratch_out_dev,
+                   const double* RHS_dev, long ld, int P, double* X_dev, double tol, int maxiter,
+                   int check_every, int* iters_host, double* resid_host, int* info_host, void* stream) {
+    LMC_REQUIRE(apply_cb && scratch_in_dev && scratch_out_dev && RHS_dev && X_dev, "null argument");
+    LMC_REQUIRE(n >= 1 && ld >= n, "bad block shape");
+    CallbackOperator A;
+    A.n = n; A.perm = nullptr; A.cb = apply_cb; A.ctx = ctx;
+    A.scratch_in = scratch_in_dev; A.scratch_out = scratch_out_dev;
+    return cg_core(A, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host, info_host,
+                   (cudaStream_t)stream);
 }
 
 int lmc_block_dot(const double* A_dev, long lda, const double* B_dev, long ldb, long n, int ncols,

@@ -71,6 +71,9 @@ int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, co
 int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
                  int check_every, int* iters, double* resid, int* istop, cudaStream_t st);
 
+int cg_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+             int check_every, int* iters, double* resid, int* info, cudaStream_t st);
+
 // tops_extra: [ntops_extra][cells] derivative tops, host memory unless extra_on_device
 int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* RINV, long ld, int N,
                int ntops_extra, const double* tops_extra, bool extra_on_device, double* quad, double* trace,

@@ -256,6 +256,21 @@ class FusedLMC:
             nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(istop)))
         return X, iters, resid, istop
 
+    def cg(self, RHS, tol=1e-4, maxiter=None, check_every=100):
+        """Batched Iterative.solve(..., minres=False) (scipy's cg behind the reference wrapper) on the
+        rows of RHS.  Returns (X, iters, resid, info)."""
+        RHS = self._block(RHS)
+        P = RHS.shape[0]
+        X = np.empty_like(RHS)
+        iters = np.zeros(P, dtype=np.int32)
+        resid = np.zeros(P, dtype=np.float64)
+        info = np.zeros(P, dtype=np.int32)
+        nat.check(nat.lib.lmc_cg_host(
+            self._h, nat.host_ptr(RHS), self.n, P, nat.host_ptr(X), float(tol),
+            int(self.n if maxiter is None else maxiter), int(check_every),
+            nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(info)))
+        return X, iters, resid, info
+
     def minres_device(self, RHS, tol=1e-4, maxiter=None, check_every=100):
         torch = nat.require_cuda()
         assert RHS.is_cuda and RHS.dtype == torch.float64 and RHS.is_contiguous()

@@ -28,6 +28,8 @@ sys.path.insert(0, '/root/reference')
 
 _orig_minres = sla.minres
 sla.minres = lambda A, b, tol=1e-5, **kw: _orig_minres(A, b, rtol=tol, **kw)
+_orig_cg = sla.cg
+sla.cg = lambda A, b, tol=1e-5, **kw: _orig_cg(A, b, rtol=tol, **kw)   # same rename for the minres=False path
 
 from runlmc.linalg.toeplitz import Toeplitz  # noqa: E402
 from runlmc.linalg.bttb import BTTB  # noqa: E402
@@ -316,6 +318,8 @@ class _ListKey(list):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'predict':
         return main_predict()
+    if len(sys.argv) > 1 and sys.argv[1] == 'cg':
+        return main_cg()
     np.savez_compressed(os.path.join(HERE, 'linalg.npz'), **linalg_cases())
     np.savez_compressed(os.path.join(HERE, 'interp.npz'), **interp_cases())
     # config A (README scale), 1-D, edge-touching inputs
@@ -333,6 +337,31 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'lmc_B.npz'),
                         **lmc_case(pb, reps=('sum',)))
     print('golden vectors written to', HERE)
+
+
+def cg_case(prob, tol=1e-4):
+    """Iterative.solve(..., minres=False): scipy's cg behind the same wrapper (iterative.py:44-51)."""
+    fk = DuckKernel(prob)
+    ad = fk.ad
+    W = ref_interp.multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    K, _ = gen_grid_kernel(fk, {ad: prob.dists}, {ad: (W, WT)}, prob.lens)
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, minres=False, tol=tol)
+    return x, np.array(ctr), np.array(err)
+
+
+def main_cg():
+    probs = {
+        'lmc_A': synthetic.make_problem('A', seed=1234, edge=True, cells_per_lengthscale=4),
+        'lmc_2d': synthetic.make_problem('e_small', seed=99, cells_per_lengthscale=3, lens=[120, 90, 100],
+                                         grid=[12, 10], N=5),
+        'lmc_B': synthetic.make_problem('B', seed=1234, lens=[400, 380], grid=[128], N=4),
+    }
+    out = {}
+    for name, prob in probs.items():
+        out[name + '_x'], out[name + '_ctr'], out[name + '_err'] = cg_case(prob)
+        print(name, 'cg callbacks', int(out[name + '_ctr']), 'residual', float(out[name + '_err']))
+    np.savez_compressed(os.path.join(HERE, 'cg.npz'), **out)
 
 
 def main_predict():

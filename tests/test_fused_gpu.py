@@ -351,3 +351,41 @@ def test_error_paths():
     op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
     with pytest.raises(ValueError):
         op.mvm(np.zeros(prob.n + 1))
+
+
+@pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
+def test_cg_against_reference_golden(name):
+    """Iterative.solve(..., minres=False): the device CG against the reference's own run
+    (tests/golden/cg.npz) and, column by column in a block, against the oracle's restated scipy loop."""
+    from test_oracle_golden import GOLDEN_PROBLEMS
+    g = load_golden('cg')
+    prob = GOLDEN_PROBLEMS[name]()
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    RHS = np.vstack([prob.y[None, :], prob.probes[:3], np.zeros((1, prob.n))])
+    X, iters, resid, info = op.cg(RHS, tol=1e-4)
+    # iteration counts: CG's own stop ||r|| < 1e-10 ||b|| sits on the recurrence residual, which
+    # rounding moves by a few iterations on the ill-conditioned case (lmc_B: 40 in the reference)
+    slack = lambda ctr: max(1, ctr // 8)   # noqa: E731
+    assert abs(int(iters[0]) - int(g[name + '_ctr'])) <= slack(int(g[name + '_ctr']))
+    assert rel_err(X[0], g[name + '_x']) < SOLVE_TOL
+    assert resid[0] <= max(1e-4, 3 * float(g[name + '_err']))
+    for b, x, it, r in zip(RHS[1:4], X[1:4], iters[1:4], resid[1:4]):
+        xr, ctr, err = orc.iterative_solve(ref.matvec, b, 1e-4, use_minres=False)
+        assert abs(int(it) - ctr) <= slack(ctr)
+        assert rel_err(x, xr) < SOLVE_TOL and r <= max(1e-4, 3 * err)
+        assert abs(np.linalg.norm(b - ref.matvec(x)) - r) <= 1e-8 * max(1.0, np.linalg.norm(b))
+    assert iters[4] == 0 and not X[4].any() and info[4] == 0          # zero right-hand side
+
+
+def test_cg_fixed_iterations_match_oracle():
+    """Iterates of the first CG steps agree with the restated scipy loop to rounding."""
+    prob = PROBLEMS['d_small']()
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    b = prob.probes[0]
+    for k in (1, 2, 5):
+        X, iters, _, info = op.cg(b, tol=1e-4, maxiter=k)
+        xr, _, _ = orc.cg(ref.matvec, b, 1e-10, k)
+        assert iters[0] == k and info[0] == k
+        assert rel_err(X[0], xr) < 1e-10

@@ -122,3 +122,19 @@ def test_generic_derivative_matches_fused():
     for a, b, r in zip(fused, generic, ref):
         assert rel_err(np.array(a), r) < 1e-8
         assert rel_err(np.array(b), r) < 1e-8
+
+
+@pytest.mark.parametrize('fuse', [True, False])
+def test_iterative_solve_cg(fuse):
+    """Iterative.solve(..., minres=False) through the fused operator and through the generic
+    operator tree (callback products), against the reference's own cg run."""
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import Iterative
+    prob, _ = golden_problem('lmc_B')
+    g = load_golden('cg')
+    fk, dists, interps, ad = build(prob, fuse)
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, minres=False, tol=1e-4)
+    assert abs(ctr - int(g['lmc_B_ctr'])) <= 5       # see test_cg_against_reference_golden
+    assert rel_err(x, g['lmc_B_x']) < 1e-5
+    assert err <= 1e-4
