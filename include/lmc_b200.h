@@ -21,6 +21,12 @@
  *    synchronise unless stated.
  *  - vectors of length n are in the caller's point order: outputs concatenated,
  *    np.hstack(Ys) (reference lmc/likelihood.py:30).
+ *  - one CUDA device per process (the model is one process per GPU; kernel attributes
+ *    are set once per process).  Handles own all their device memory, including the
+ *    solver state kept between solves, and are independent of each other: different
+ *    handles may be driven from different host threads, one handle from one thread at a
+ *    time.  lmc_last_error() is per host thread; the launch counter and the profiling
+ *    switch are process-wide diagnostics.
  */
 #ifndef LMC_B200_H
 #define LMC_B200_H

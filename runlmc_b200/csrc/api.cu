@@ -60,7 +60,7 @@ extern "C" {
 
 int lmc_version(void) { return 100; }
 const char* lmc_last_error(void) { return get_error(); }
-unsigned long long lmc_launch_count(void) { return g_launches; }
+unsigned long long lmc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int lmc_op_create(lmc_op** out, int D, int ndim, const int* grid_sizes, const double* origin,
                   const double* delta, const int* lens, const double* X_host) {

@@ -1,6 +1,7 @@
 // Shared declarations for the sm_100a SKI-LMC kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -38,8 +39,8 @@ const char* get_error();
     } while (0)
 
 // kernel launch counter (bench.py reports gpu_launches from it)
-extern unsigned long long g_launches;
-inline void count_launch(int k = 1) { g_launches += (unsigned long long)k; }
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int k = 1) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
 
 // Optional per-kernel-family timing with CUDA events on the launching stream
 // (bench.py's roofline figures come from here).  Disabled => zero overhead.

@@ -313,12 +313,23 @@ __global__ void __launch_bounds__(kVecThreads) scale_cols_kernel(const double* _
     }
 }
 
+// Solver workspace: grow-only, owned by whoever owns the operator (the fused handle keeps it between
+// solves; a callback operator's lives for one call)
+static int reserve_workspace(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return 0;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    LMC_CHECK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return 0;
+}
 // The product the solver iterates with: out = A (in * in_scale) on [P][n] blocks
 struct MinresOperator {
     long n = 0;
     const int* perm = nullptr;  // solver order -> caller order (nullptr = identity)
     virtual int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
                       cudaStream_t st) = 0;
+    // device memory for the solver's state vectors, valid until the operator goes away
+    virtual int workspace(size_t bytes, void** p) = 0;
     virtual ~MinresOperator() {}
 };
 
@@ -335,6 +346,11 @@ struct FusedOperator : MinresOperator {
         cv.in_scale = in_scale; cv.active = active;
         return op_mvm(op, cv, st);
     }
+    int workspace(size_t bytes, void** p) override {
+        LMC_TRY(reserve_workspace(&op->solver_ws, &op->solver_ws_cap, bytes));
+        *p = op->solver_ws;
+        return 0;
+    }
 };
 
 // Operator trees composed on the Python side: the solver fills `scratch_in`,
@@ -344,6 +360,14 @@ struct CallbackOperator : MinresOperator {
     void* ctx;
     double* scratch_in;
     double* scratch_out;
+    void* ws = nullptr;
+    size_t ws_cap = 0;
+    ~CallbackOperator() override { cudaFree(ws); }
+    int workspace(size_t bytes, void** p) override {
+        LMC_TRY(reserve_workspace(&ws, &ws_cap, bytes));
+        *p = ws;
+        return 0;
+    }
     int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
               cudaStream_t st) override {
         (void)active;
@@ -366,21 +390,6 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
-// Solver workspace kept between calls (grow-only): cudaMalloc/cudaFree of ~8 n P doubles per solve
-// would otherwise cost as much as tens of iterations.
-struct Workspace {
-    void* p = nullptr;
-    size_t cap = 0;
-    ~Workspace() { if (p) cudaFree(p); }
-    int reserve(size_t bytes) {
-        if (bytes <= cap) return 0;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        LMC_CHECK(cudaMalloc(&p, bytes));
-        cap = bytes;
-        return 0;
-    }
-};
-static Workspace g_ws;
 struct WsSlice {
     char* p;
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
@@ -398,9 +407,10 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
     const size_t vec = sizeof(double) * (size_t)P * n;
     DevBuf parts[3], stb, invb, act, nact;
     const size_t vec_al = (vec + 255) & ~(size_t)255;
-    LMC_TRY(g_ws.reserve(vec_al * 8));
+    void* ws = nullptr;
+    LMC_TRY(A.workspace(vec_al * 8, &ws));
     WsSlice bufs[8];
-    for (int i = 0; i < 8; ++i) bufs[i].p = static_cast<char*>(g_ws.p) + vec_al * i;
+    for (int i = 0; i < 8; ++i) bufs[i].p = static_cast<char*>(ws) + vec_al * i;
     for (auto& b : parts) LMC_TRY(b.alloc(sizeof(double) * (size_t)P * nblk));
     LMC_TRY(stb.alloc(sizeof(ColState) * P));
     LMC_TRY(invb.alloc(sizeof(double) * P));
@@ -645,9 +655,10 @@ static int cg_core(MinresOperator& A, const double* RHS, long ld, int P, double*
     const double rtol = std::fmin(1e-10, tol);
     const size_t vec = sizeof(double) * (size_t)P * n;
     const size_t vec_al = (vec + 255) & ~(size_t)255;
-    LMC_TRY(g_ws.reserve(vec_al * 5));
+    void* ws = nullptr;
+    LMC_TRY(A.workspace(vec_al * 5, &ws));
     WsSlice bufs[5];
-    for (int i = 0; i < 5; ++i) bufs[i].p = static_cast<char*>(g_ws.p) + vec_al * i;
+    for (int i = 0; i < 5; ++i) bufs[i].p = static_cast<char*>(ws) + vec_al * i;
     double *b = bufs[0].as<double>(), *x = bufs[1].as<double>(), *r = bufs[2].as<double>();
     double *p = bufs[3].as<double>(), *q = bufs[4].as<double>();
     DevBuf parts[2], stb, act, nact;

@@ -13,10 +13,10 @@
 
 namespace lmc {
 
-static std::string g_err;
+static thread_local std::string g_err;   // per host thread, like errno
 void set_error(const std::string& s) { g_err = s; }
 const char* get_error() { return g_err.c_str(); }
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 bool g_prof_on = false;
 namespace {
@@ -151,6 +151,7 @@ lmc_op::~lmc_op() {
     cudaFree(G);
     cudaFree(S);
     cudaFree(Vs);
+    cudaFree(solver_ws);
 }
 
 lmc_bttb::~lmc_bttb() {

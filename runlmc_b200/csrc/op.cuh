@@ -41,6 +41,10 @@ struct lmc_op {
     double* stage_in[2] = {nullptr, nullptr};
     double* stage_out[2] = {nullptr, nullptr};
     size_t stage_cap = 0;   // doubles per staging buffer
+    // block-solver state vectors (MINRES: 8 [P][n] blocks, CG: 5), grow-only, kept between solves:
+    // cudaMalloc/cudaFree of ~8 n P doubles per solve would cost as much as tens of iterations
+    void* solver_ws = nullptr;
+    size_t solver_ws_cap = 0;
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     ~lmc_op();

@@ -178,7 +178,7 @@ static int launch_fused_kernel(const FusedArgs& a, const MIX& m, dim3 grid, int 
 template <int D, int NQ>
 static int launch_fused_lowrank(const FusedArgs& a, const MixSpec& mix, dim3 grid, int threads, size_t smem,
                                 cudaStream_t st) {
-    static MixLR<D, NQ> ml;   // zero-initialised
+    MixLR<D, NQ> ml = {};     // kernel parameter, copied at launch
     int r = 0;
     for (int q = 0; q < a.Q; ++q) {
         ml.rank[q] = mix.ranks[q];
@@ -225,7 +225,7 @@ int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, in
             default: rc = launch_fused_lowrank<D, 8>(a, mix, grid, threads, smem, st); break;
         }
     } else {
-        static MixB<D> mb;   // zero-initialised; only the first Q blocks are read
+        MixB<D> mb = {};     // kernel parameter; only the first Q blocks are read
         for (int q = 0; q < a.Q; ++q)
             for (int i = 0; i < D; ++i)
                 for (int j = 0; j < D; ++j) mb.b[q][i][j] = mix.B[((size_t)q * D + i) * D + j];

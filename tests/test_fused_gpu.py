@@ -389,3 +389,22 @@ def test_cg_fixed_iterations_match_oracle():
         xr, _, _ = orc.cg(ref.matvec, b, 1e-10, k)
         assert iters[0] == k and info[0] == k
         assert rel_err(X[0], xr) < 1e-10
+
+
+def test_two_handles_from_two_threads():
+    """Handles own their solver state: two operators solving at the same time from two host
+    threads (ctypes releases the GIL) give the results of the same solves run one after the other."""
+    import threading
+    pa, pb = PROBLEMS['d_small'](), PROBLEMS['2d_edge']()
+    oa, ob = fused_from_problem(pa), fused_from_problem(pb)
+    Ra = np.vstack([pa.y[None, :], pa.probes[:4]])
+    Rb = np.vstack([pb.y[None, :], pb.probes[:3]])
+    want_a, want_b = oa.minres(Ra, tol=1e-4), ob.cg(Rb, tol=1e-4)
+    got = {}
+    for rep in range(3):
+        ta = threading.Thread(target=lambda: got.__setitem__('a', oa.minres(Ra, tol=1e-4)))
+        tb = threading.Thread(target=lambda: got.__setitem__('b', ob.cg(Rb, tol=1e-4)))
+        ta.start(); tb.start(); ta.join(); tb.join()
+        for k, want in (('a', want_a), ('b', want_b)):
+            np.testing.assert_array_equal(got[k][0], want[0])     # deterministic kernels, private state
+            np.testing.assert_array_equal(got[k][1], want[1])
