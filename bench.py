@@ -336,6 +336,18 @@ def run_own(args):
                     'unit': 'GB/s', 'frac': b_mvm / ms_step / 1e6 / peak,
                     'note': 'whole product vs B_mvm = 16nP + 8dn + 8Q*bins + 8D (SURVEY.md sec.8d), this rank'}
 
+    # ---- the spectral stage against the fp64 roofline: pruned FFTs
+    # 2 * D * 2.5 * M~ log2 M~ * 3/4 plus the mix 4 D^2 bins flops per MVM and RHS ----
+    fp64 = np.zeros(1)
+    nat.check(nat.lib.lmc_fp64_peak(nat.host_ptr(fp64)))
+    spectral_ms = sum(f['ms_per_step'] for f in fams if f['family'].startswith('fft') or f['family'] == 'mix')
+    flops_rhs = 2.0 * prob.D * 2.5 * bins * np.log2(bins) * 0.75 + 4.0 * prob.D ** 2 * bins
+    roofline_fp64 = {'bound': 'fp64', 'stage': 'fft + mix + inverse fft', 'alg_flops_per_step': flops_rhs * P,
+                     'achieved': flops_rhs * P / (spectral_ms * 1e-3) / 1e12 if spectral_ms else None,
+                     'peak': float(fp64[0]), 'unit': 'TFLOP/s',
+                     'frac': flops_rhs * P / (spectral_ms * 1e-3) / 1e12 / float(fp64[0]) if spectral_ms else None,
+                     'peak_source': 'measured (lmc_fp64_peak: DFMA microbenchmark on this GPU)'}
+
     # ---- one full stochastic gradient evaluation (solves + all partials) ----
     grad = None
     if not args.no_grad:
@@ -356,6 +368,17 @@ def run_own(args):
                 'minres_iter_rhs_per_s': stats['iterations'] * (prob.N + 1) / dt,
                 'includes': 'host->device copies of y/probes, N+1 MINRES solves (tol 1e-4, reference stopping rules), '
                             'all partial derivatives, allreduce'}
+        # MINRES against B_minres_iter = 120 n bytes per iteration and RHS
+        it_rate = grad['minres_iter_rhs_per_s'] / world
+        grad['roofline_minres'] = {'bound': 'hbm', 'alg_bytes_per_iter_rhs': 120.0 * prob.n,
+                                   'achieved': 120.0 * prob.n * it_rate / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                   'frac': 120.0 * prob.n * it_rate / 1e9 / peak, 'note': 'per GPU'}
+        if cpu is not None:
+            # the reference's path for the same evaluation: (N+1) solves x mean iterations products, on
+            # all host cores at the measured CPU product rate (solver vector work and partials not counted)
+            cpu_s = (prob.N + 1) * stats['iterations'] / cpu['value']
+            cpu['grad_eval_seconds_extrapolated'] = cpu_s
+            cpu['grad_evals_per_s_extrapolated'] = 1.0 / cpu_s
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
@@ -363,7 +386,8 @@ def run_own(args):
                 'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': io_bytes, 'd2h_bytes_per_step': io_bytes,
                         'steps': e2e_steps, 'api': 'FusedLMC.mvm_into -> lmc_mvm_host (pinned host buffers, '
                         'chunked copy/compute/copy pipeline)', 'max_abs_diff_vs_resident': e2e_check}, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
-                'roofline_mvm': roofline_mvm, 'kernel_families': fams, 'gradient': grad}
+                'roofline_mvm': roofline_mvm, 'roofline_fp64': roofline_fp64, 'kernel_families': fams,
+                'gradient': grad}
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))

@@ -43,6 +43,10 @@ const char* lmc_last_error(void);
 /* number of CUDA kernels launched by this library so far in this process */
 unsigned long long lmc_launch_count(void);
 
+/* Measured dense fp64 FMA rate of the current GPU in TFLOP/s (a register-resident DFMA
+ * microbenchmark, best of 5): the compute roofline bench.py holds the FFT + mix stage against. */
+int lmc_fp64_peak(double* tflops_host);
+
 /* Optional per-kernel-family device timing (CUDA events on the launching stream).
  * lmc_profile_begin() starts recording; lmc_profile_end() synchronises and returns,
  * per family, total milliseconds and launch counts (arrays of lmc_profile_ncat()). */

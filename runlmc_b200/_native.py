@@ -36,6 +36,7 @@ SIGNATURES = {
     'lmc_version': (_i, []),
     'lmc_last_error': (ctypes.c_char_p, []),
     'lmc_launch_count': (ctypes.c_ulonglong, []),
+    'lmc_fp64_peak': (_i, [_p]),
     'lmc_profile_ncat': (_i, []),
     'lmc_profile_name': (ctypes.c_char_p, [_i]),
     'lmc_profile_begin': (_i, []),

@@ -104,6 +104,53 @@ int lmc_csr_apply(int rows, const int* indptr_dev, const int* indices_dev, const
     return 0;
 }
 
+// ---- fp64 FMA rate of this GPU (the second roofline of the spectral stage) ----
+// 8 independent DFMA chains per thread, 4096 rounds: 2 * 8 * 4096 flops per thread
+__global__ void __launch_bounds__(256) fp64_fma_kernel(double* out, double a, double b, int rounds) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (double)(threadIdx.x + i) * 1e-3;
+    for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;   // keeps the chains alive, never true in practice
+}
+
+int lmc_fp64_peak(double* tflops_host) {
+    LMC_REQUIRE(tflops_host, "null argument");
+    int dev = 0, sms = 0;
+    LMC_CHECK(cudaGetDevice(&dev));
+    LMC_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    LMC_CHECK(cudaMalloc(&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    LMC_CHECK(cudaEventCreate(&e0));
+    LMC_CHECK(cudaEventCreate(&e1));
+    const int rounds = 4096, blocks = sms * 8, reps = 5;
+    double best = 0.0;
+    for (int rep = 0; rep < reps + 1; ++rep) {   // first pass warms up
+        LMC_CHECK(cudaEventRecord(e0, 0));
+        fp64_fma_kernel<<<blocks, 256>>>(out, 0.999999, 1e-7, rounds);
+        LMC_CHECK(cudaEventRecord(e1, 0));
+        LMC_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        LMC_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8 * rounds * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    count_launch(reps + 1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    LMC_CHECK(cudaGetLastError());
+    *tflops_host = best;
+    return 0;
+}
+
 int lmc_axpby(long len, double a, const double* X_dev, double b, double* Y_dev, void* stream) {
     if (len <= 0) return 0;
     axpby_kernel<<<ceil_div(len, 256), 256, 0, (cudaStream_t)stream>>>(len, a, X_dev, b, Y_dev);
