@@ -67,6 +67,10 @@ class Iterative:
         non-convergence, logs instead.
 
         :return: x, and (iterations, error) too if verbose"""
+        if getattr(K, 'preconditioner', None) is not None:
+            # the reference forwards it to scipy as M (iterative.py:47) but nothing in runlmc ever sets
+            # it; the device solvers implement M = I only, so say so instead of ignoring it
+            raise NotImplementedError('preconditioned solves are not part of the accelerated path')
         y = np.asarray(y, dtype=np.float64)
         X, iters, resid, istop = solve_block(K, y.reshape(1, -1), tol=tol, minres=minres)
         n = K.shape[0]

@@ -271,7 +271,7 @@ struct Scatter1Smem {
 };
 
 template <int G, int CAP>
-__global__ void __launch_bounds__(256, 2) to_grid_1d_v3_kernel(const InterpArgs a) {
+__global__ void __launch_bounds__(256, CAP <= 256 ? 4 : 2) to_grid_1d_v3_kernel(const InterpArgs a) {
     typedef Scatter1Smem<G, CAP> Smem;
     constexpr int NBIN = 256 / G, TC = NBIN - 3, VP = G + 1;
     static_assert(CAP <= 512 && 8 * NBIN * G <= 2 * CAP * VP, "staging / exchange layout");
@@ -1067,14 +1067,21 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
     a.G = G;
     const int npairs = (cv.ncols + 1) / 2;
     if (ps.ndim == 1) {
-        constexpr int G1 = 8, CAP1 = 512;
+        constexpr int G1 = 8, CAP1 = 512, CAP1S = 256;
         typedef Scatter1Smem<G1, CAP1> Smem;
+        typedef Scatter1Smem<G1, CAP1S> SmemS;
         static bool attr = false;
-        if (!attr) { LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1>, sizeof(Smem))); attr = true; }
+        static const int cap_sel = env_int("LMC_TG1_CAP", CAP1S);   // 256: four CTAs per SM (0.125 -> 0.101 ms at config D)
+        if (!attr) {
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1>, sizeof(Smem)));
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1S>, sizeof(SmemS)));
+            attr = true;
+        }
         const int TC = 256 / G1 - 3;
         a.tiles = ceil_div(ps.m[0], TC);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
-        to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
+        if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S><<<grid, 256, sizeof(SmemS), st>>>(a);
+        else to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
     } else if (kind == SCATTER_G16) {
         LMC_TRY((launch_strips<16, 8, 8, kCap16>(ps, a, npairs, st)));
     } else if (kind == SCATTER_G8) {

@@ -138,3 +138,15 @@ def test_iterative_solve_cg(fuse):
     assert abs(ctr - int(g['lmc_B_ctr'])) <= 5       # see test_cg_against_reference_golden
     assert rel_err(x, g['lmc_B_x']) < 1e-5
     assert err <= 1e-4
+
+
+def test_preconditioner_is_refused_loudly():
+    """iterative.py:47 forwards K.preconditioner to scipy; the device solvers are M = I only."""
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import Iterative
+    prob, _ = golden_problem('lmc_A')
+    fk, dists, interps, ad = build(prob)
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    K.preconditioner = K
+    with pytest.raises(NotImplementedError):
+        Iterative.solve(K, prob.y)
