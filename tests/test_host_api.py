@@ -167,3 +167,41 @@ def test_allreduce_trace_gloo_world2():
         np.testing.assert_allclose(trace, per_probe.sum(axis=0), rtol=1e-13)
         np.testing.assert_allclose(ntrace, per_probe[:, 0, 0].sum(axis=0), rtol=1e-13)
         assert it == 10.0 and rs == 5.0
+
+
+def test_device_kernel_selection_rules():
+    """gen_grid_kernel hands kernel evaluation to the device only for its own RBF / Matern32 /
+    StdPeriodic classes on the operator's own grid distances (host logic, no GPU needed)."""
+    from runlmc_b200 import kern
+    from runlmc_b200.fused import kernel_descriptor, KERNEL_KINDS
+    from runlmc_b200.lmc.grid_kernel import _device_kernels
+    from runlmc_b200.lmc.functional_kernel import FunctionalKernel
+
+    assert kernel_descriptor(kern.RBF(2.0)) == (KERNEL_KINDS['RBF'], 2.0, 1.0)
+    assert kernel_descriptor(kern.Matern32(0.5)) == (KERNEL_KINDS['Matern32'], 0.5, 1.0)
+    assert kernel_descriptor(kern.StdPeriodic(3.0, 0.25)) == (KERNEL_KINDS['StdPeriodic'], 3.0, 0.25)
+
+    class MyRBF(kern.RBF):           # a subclass may override from_dist: evaluated on the host
+        pass
+    assert kernel_descriptor(MyRBF(1.0)) is None
+
+    class FakeFused:
+        def __init__(self, d):
+            self._d = d
+
+        def grid_dists(self):
+            return self._d
+
+    dists = np.linspace(0, 1, 33)
+    fk = FunctionalKernel(D=2, lmc_kernels=[kern.RBF(1.0), kern.StdPeriodic(1.0, 0.5)], lmc_ranks=[1, 1])
+    fk.set_input_dim(1)
+    assert _device_kernels(fk, [0, 1], FakeFused(dists), dists) is not None
+    assert _device_kernels(fk, [0, 1], FakeFused(dists), dists * (1 + 1e-9)) is None      # foreign distances
+    assert _device_kernels(fk, [0, 1], FakeFused(dists), dists[:-1]) is None
+    fk2 = FunctionalKernel(D=2, lmc_kernels=[MyRBF(1.0)], lmc_ranks=[1])
+    fk2.set_input_dim(1)
+    assert _device_kernels(fk2, [0], FakeFused(dists), dists) is None                     # foreign kernel class
+
+    class Duck:                      # FunctionalKernel stand-ins without `_kernels` keep the uploaded tops
+        pass
+    assert _device_kernels(Duck(), [0], FakeFused(dists), dists) is None
