@@ -408,3 +408,36 @@ def test_two_handles_from_two_threads():
         for k, want in (('a', want_a), ('b', want_b)):
             np.testing.assert_array_equal(got[k][0], want[0])     # deterministic kernels, private state
             np.testing.assert_array_equal(got[k][1], want[1])
+
+
+@pytest.mark.parametrize('base,Q,ranks', [
+    ('d_small', 1, [1]), ('d_small', 5, [1, 2, 1, 2, 1]), ('d_small', 7, [1] * 7), ('d_small', 3, [3, 1, 2]),
+    ('e_small', 1, [2]), ('e_small', 5, [2, 1, 1, 2, 1]), ('e_small', 6, [1, 1, 3, 1, 1, 1]),
+])
+def test_many_kernels_and_higher_ranks(base, Q, ranks):
+    """Q = 1, Q > 4 (run-time kernel count in the fused mix) and coregionalisation ranks 1..3 (rank 3
+    takes the dense mix) against the oracle, with and without the low-rank factors; products,
+    a few solver iterations and the gradient Gram stage."""
+    from runlmc_b200.fused import FusedLMC, assemble_gradients
+    prob = synthetic.make_problem(base, seed=31, cells_per_lengthscale=4, Q=Q)
+    rng = np.random.default_rng(7)
+    prob.coreg_vecs = [rng.uniform(-1, 1, size=(r, prob.D)) for r in ranks]
+    spec, ref = oracle_from_problem(prob)
+    V = rng.standard_normal((5, prob.n))
+    want = np.array([ref.matvec(v) for v in V])
+    ops = []
+    for factors in (True, False):
+        op = fused_from_problem(prob, factors=factors)
+        assert rel_err(op.mvm(V), want) < MVM_TOL
+        ops.append(op)
+    X, iters, _, _ = ops[0].minres(V[:2], tol=1e-4, maxiter=4)
+    for b, x in zip(V[:2], X):
+        xr, _, _, _ = orc.minres(ref.matvec, b, 1e-10, 4)
+        assert rel_err(x, xr) < 1e-9
+    # Gram stage: identical inputs, low-rank vs dense operator and the oracle's gradient of the same
+    alpha, R, RINV = V[0], prob.probes[:4], V[1:5]
+    extra = [t for ts in prob.top_grads for t in ts]
+    g0 = ops[0].grad_grams(alpha, R, RINV, extra)
+    g1 = ops[1].grad_grams(alpha, R, RINV, extra)
+    for a, b in zip(g0, g1):
+        assert rel_err(a, b) < 1e-11
