@@ -140,7 +140,9 @@ int lmc_op_perm(const lmc_op* op, int* perm_host) {
 }
 
 int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream) {
-    LMC_REQUIRE(op && V_dev && OUT_dev, "null argument");
+    LMC_REQUIRE(op, "null argument");
+    if (P == 0) return 0;   // an empty block has no storage to point at
+    LMC_REQUIRE(V_dev && OUT_dev, "null argument");
     LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
     LMC_REQUIRE(V_dev != OUT_dev, "in-place product not supported");
     ColumnView cv;
@@ -149,7 +151,9 @@ int lmc_mvm(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, vo
 }
 
 int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream) {
-    LMC_REQUIRE(op && V_dev && OUT_dev, "null argument");
+    LMC_REQUIRE(op, "null argument");
+    if (P == 0) return 0;   // an empty block has no storage to point at
+    LMC_REQUIRE(V_dev && OUT_dev, "null argument");
     LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
     LMC_REQUIRE(V_dev != OUT_dev, "in-place product not supported");
     ColumnView cv;
@@ -162,10 +166,11 @@ int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_
 // staging, so PCIe traffic in both directions overlaps the kernels.  With pinned host memory the
 // copies are truly asynchronous; pageable memory works too (the driver stages it).
 int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_host) {
-    LMC_REQUIRE(op && V_host && OUT_host, "null argument");
+    LMC_REQUIRE(op, "null argument");
+    if (P == 0) return 0;
+    LMC_REQUIRE(V_host && OUT_host, "null argument");
     LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
-    if (P == 0) return 0;
     const long n = op->ps.n;
     // chunk width: even, ~64 MB per buffer, at least 2 and at most 32 columns
     int chunk = (int)std::max<long>(2, std::min<long>(32, (64L << 20) / (8 * n)));

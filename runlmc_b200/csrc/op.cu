@@ -88,6 +88,7 @@ int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st) {
 
 int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
+    if (cv.ncols == 0) return 0;   // an empty block is a valid product (Matrix.matmat of an [n, 0] array)
     LMC_TRY(op_ensure_workspace(op));
     const int npairs = (cv.ncols + 1) / 2;
     const long n = op->ps.n;

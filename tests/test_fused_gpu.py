@@ -351,6 +351,11 @@ def test_error_paths():
     op.set_params(prob.tops, prob.coreg_mats(), prob.noise)
     with pytest.raises(ValueError):
         op.mvm(np.zeros(prob.n + 1))
+    import torch
+    empty = torch.empty((0, prob.n), dtype=torch.float64, device='cuda')
+    assert op.mvm_device(empty).shape == (0, prob.n)          # empty blocks are valid products
+    assert op.mvm_sorted_device(empty).shape == (0, prob.n)
+    assert op.mvm(np.zeros((0, prob.n))).shape == (0, prob.n)
 
 
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
