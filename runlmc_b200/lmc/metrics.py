@@ -1,9 +1,2 @@
-class Metrics:
-    """Per-iteration statistics (reference runlmc/lmc/metrics.py:4-10)."""
-
-    def __init__(self):
-        self.iterations = []
-        self.grad_norms = []
-        self.grad_error = []
-        self.solv_error = []
-        self.log_likely = []
+"""runlmc.lmc.metrics: `Metrics` is defined next to the service that fills it, stochastic_deriv.py."""
+from .stochastic_deriv import Metrics  # noqa: F401

@@ -1,10 +1,36 @@
 """Mirror of runlmc/lmc/stochastic_deriv.py: Hutchinson-probe derivative service."""
 import numpy as np
 
-from .derivative import Derivative
 from ..approx.iterative import Iterative, fused_of, solve_block
 from .. import _native as nat
 from .. import device as dev
+
+
+class Derivative:
+    """A log-likelihood derivative in the two pieces every estimator provides: the data-fit term
+    alpha' dK alpha and the log-determinant term tr(K^-1 dK); dL/dtheta is half their difference
+    (reference lmc/derivative.py:5-12)."""
+
+    def d_normal_quadratic(self, dKdt):
+        raise NotImplementedError
+
+    def d_logdet_K(self, dKdt):
+        raise NotImplementedError
+
+    def derivative(self, dKdt):
+        fit, logdet = self.d_normal_quadratic(dKdt), self.d_logdet_K(dKdt)
+        return (fit - logdet) / 2
+
+
+class Metrics:
+    """What a run records per optimiser step when asked to (reference lmc/metrics.py:4-10): solver
+    iterations and residuals from the derivative service, gradient norms / errors and the
+    log-likelihood from the model."""
+    FIELDS = ('iterations', 'grad_norms', 'grad_error', 'solv_error', 'log_likely')
+
+    def __init__(self):
+        for name in self.FIELDS:
+            setattr(self, name, [])
 
 
 class StochasticDerivService:
