@@ -205,3 +205,30 @@ def test_device_kernel_selection_rules():
     class Duck:                      # FunctionalKernel stand-ins without `_kernels` keep the uploaded tops
         pass
     assert _device_kernels(Duck(), [0], FakeFused(dists), dists) is None
+
+
+def test_kernel_formulas_and_parameter_gradients():
+    """runlmc_b200.kern (the formulas the device kernel evaluation restates, csrc/setup.cu): values
+    at known points and parameter derivatives against central differences."""
+    from runlmc_b200 import kern
+    r = np.linspace(0.0, 2.5, 41)
+    k = kern.RBF(3.0)
+    np.testing.assert_allclose(k.from_dist(r), np.exp(-1.5 * r ** 2), rtol=1e-15)
+    m = kern.Matern32(0.7)
+    np.testing.assert_allclose(m.from_dist(r), (1 + np.sqrt(3) * 0.7 * r) * np.exp(-np.sqrt(3) * 0.7 * r), rtol=1e-14)
+    p = kern.StdPeriodic(2.0, 0.8)
+    np.testing.assert_allclose(p.from_dist(r), np.exp(-np.sin(np.pi * r / 0.8) ** 2), rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(p.from_dist(r + 0.8), p.from_dist(r), rtol=1e-9, atol=1e-12)     # period
+    assert k.from_dist(0.0) == m.from_dist(0.0) == p.from_dist(0.0) == 1.0
+
+    def fd(make, params, i, h=1e-6):
+        lo, hi = list(params), list(params)
+        lo[i] -= h
+        hi[i] += h
+        return (make(*hi).from_dist(r) - make(*lo).from_dist(r)) / (2 * h)
+
+    for make, params in ((kern.RBF, [3.0]), (kern.Matern32, [0.7]), (kern.StdPeriodic, [2.0, 0.8])):
+        grads = make(*params).kernel_gradient(r)
+        assert len(grads) == len(params) == len(make(*params).param_values())
+        for i, g in enumerate(grads):
+            np.testing.assert_allclose(g, fd(make, params, i), rtol=2e-6, atol=2e-8)
