@@ -446,3 +446,39 @@ def test_many_kernels_and_higher_ranks(base, Q, ranks):
     g1 = ops[1].grad_grams(alpha, R, RINV, extra)
     for a, b in zip(g0, g1):
         assert rel_err(a, b) < 1e-11
+
+
+@pytest.mark.parametrize('ndim', [1, 2])
+def test_dense_and_clustered_points_against_oracle(ndim):
+    """Point sets far denser than the tiled kernels' shared-memory capacities, with thousands of
+    points inside single cells and at the grid edge: the 1-D scatter streams a tile in several
+    chunks, the 2-D scatter/gather fall back to their capacity-free kernels.  Products, both
+    interpolation stages and the first solver iterates against the oracle."""
+    import torch
+    rng = np.random.default_rng(17)
+    if ndim == 1:
+        prob = synthetic.make_problem('d_small', seed=5, cells_per_lengthscale=6,
+                                      lens=[4000, 3000, 10, 2500], grid=[64], N=3)
+        prob.Xs[0][:1500] = 0.5 + 0.01 * rng.uniform(size=(1500, 1))          # inside one cell
+        prob.Xs[3][:800] = 1.0 - 1e-3 * rng.uniform(size=(800, 1))            # clamped stencils at the edge
+    else:
+        prob = synthetic.make_problem('e_small', seed=6, cells_per_lengthscale=3,
+                                      lens=[3000, 2500, 2800], grid=[12, 10], N=3)
+        prob.Xs[0][:2000] = np.array([0.41, 0.63]) + 0.02 * rng.uniform(size=(2000, 2))
+        prob.Xs[2][:600] = np.array([0.999, 0.001]) + 1e-3 * rng.uniform(-1, 0, size=(600, 2)) * [1, -1]
+    _, ref = oracle_from_problem(prob)
+    V = rng.standard_normal((5, prob.n))
+    G = rng.standard_normal((3, prob.D * ref.m))
+    want = np.array([ref.matvec(v) for v in V])
+    from runlmc_b200.fused import FusedLMC
+    for build in ('device', 'host'):
+        op = FusedLMC(prob.Xs, prob.grids, build=build)
+        op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+        assert rel_err(op.mvm(V), want) < MVM_TOL
+        Vd, Gd = torch.as_tensor(V, device='cuda'), torch.as_tensor(G, device='cuda')
+        assert rel_err(op.to_grid_device(Vd).cpu().numpy(), np.array([ref.WT.dot(v) for v in V])) < 1e-12
+        assert rel_err(op.from_grid_device(Gd).cpu().numpy(), np.array([ref.W.dot(g) for g in G])) < 1e-12
+    X, iters, _, _ = op.minres(V[:2], tol=1e-4, maxiter=5)
+    for b, x in zip(V[:2], X):
+        xr, _, _, _ = orc.minres(ref.matvec, b, 1e-10, 5)
+        assert rel_err(x, xr) < 1e-9
