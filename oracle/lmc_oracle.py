@@ -342,7 +342,7 @@ class LmcOperator:
     ``sum`` starting from 0)."""
 
     def __init__(self, W, WT, Bs, tops, sizes, noise, lens, coreg_vecs=None,
-                 coreg_diags=None, rep='sum'):
+                 coreg_diags=None, rep='sum', slfm_identity=(False, False)):
         self.W, self.WT = W, WT
         self.Bs = [np.asarray(B, dtype=float) for B in Bs]
         self.sizes = [int(s) for s in sizes]
@@ -362,6 +362,9 @@ class LmcOperator:
                 tot_rank = sum(len(a) for a in coreg_vecs)
                 rep = 'slfm' if tot_rank + self.D < self.D ** 2 else 'bt'
         self.rep = rep
+        # grid_kernel.py:84-86 / 101-103: with no non-independent kernel the coreg part of the slfm
+        # representation is Identity(D m); with neither LMC nor independent kernels the diag part is
+        self._coreg_identity, self._diag_identity = slfm_identity
         D = self.D
         if rep == 'bt':
             # grid_kernel.py:115-123: one BTTB per (i <= j) block
@@ -414,15 +417,21 @@ class LmcOperator:
 
     def _grid_slfm(self, g):
         m = self.m
-        # Composition([left, toeps, right]) applied right-to-left
-        x = self._kron_with_identity(self._astar.T, g)
-        y = np.empty(len(self._slfm_specs) * m)
-        for r, sp in enumerate(self._slfm_specs):     # block_diag.py:36-40
-            y[r * m:(r + 1) * m] = self._bttb(sp, x[r * m:(r + 1) * m])
-        coreg = self._kron_with_identity(self._astar, y)
-        diag = np.empty(self.D * m)
-        for d, sp in enumerate(self._diag_specs):
-            diag[d * m:(d + 1) * m] = self._bttb(sp, g[d * m:(d + 1) * m])
+        if self._coreg_identity:
+            coreg = g
+        else:
+            # Composition([left, toeps, right]) applied right-to-left
+            x = self._kron_with_identity(self._astar.T, g)
+            y = np.empty(len(self._slfm_specs) * m)
+            for r, sp in enumerate(self._slfm_specs):     # block_diag.py:36-40
+                y[r * m:(r + 1) * m] = self._bttb(sp, x[r * m:(r + 1) * m])
+            coreg = self._kron_with_identity(self._astar, y)
+        if self._diag_identity:
+            diag = g
+        else:
+            diag = np.empty(self.D * m)
+            for d, sp in enumerate(self._diag_specs):
+                diag[d * m:(d + 1) * m] = self._bttb(sp, g[d * m:(d + 1) * m])
         return 0 + coreg + diag
 
     def grid_matvec(self, g, Bs=None, specs=None):
@@ -445,10 +454,30 @@ class LmcOperator:
     def dense(self):
         return matmat_by_columns(self.matvec, np.identity(self.n), self.n)
 
+    def diagonal(self):
+        """diag(K~) without forming K~: K_ii = noise_d + sum_q B_q[d, d] w_i' T_q w_i with w_i the
+        (at most 4^d) interpolation weights of point i.  Test oracle of the Jacobi preconditioner
+        (not a reference function: the reference only forwards K.preconditioner, iterative.py:47)."""
+        W = self.W.tocsr()
+        out = np.array(self.noise_rep, dtype=float)
+        starts = np.concatenate([[0], np.cumsum(self.lens)])
+        sizes = np.array(self.sizes)
+        for i in range(self.n):
+            d = int(np.searchsorted(starts, i, side='right') - 1)
+            cols = W.indices[W.indptr[i]:W.indptr[i + 1]] - d * self.m
+            w = W.data[W.indptr[i]:W.indptr[i + 1]]
+            idx = np.array(np.unravel_index(cols, sizes)).T             # [nnz, ndim]
+            off = np.abs(idx[:, None, :] - idx[None, :, :])
+            flat = np.ravel_multi_index(tuple(off[..., a] for a in range(len(sizes))), sizes)
+            ww = np.outer(w, w)
+            for B, top in zip(self.Bs, self.tops):
+                out[i] += B[d, d] * np.sum(ww * top[flat])
+        return out
 
-def build_operator(spec, Xs, grids, rep='auto'):
+
+def build_operator(spec, Xs, grids, rep='auto', slfm_identity=(False, False)):
     """gen_grid_kernel (grid_kernel.py:49-74) for one active-dim group; grid
-    distances as interpolated_llgp.py:415-431."""
+    distances as interpolated_llgp.py:415-431.  ``slfm_identity``: see LmcOperator."""
     W = multi_interpolant_csr(Xs, *grids)
     WT = W.transpose().tocsr()
     mesh = np.stack(np.meshgrid(*grids, indexing='ij'), axis=-1)
@@ -457,7 +486,7 @@ def build_operator(spec, Xs, grids, rep='auto'):
     lens = [len(X) for X in Xs]
     op = LmcOperator(W, WT, spec.coreg_mats(), spec.tops(dists),
                      dists.shape, spec.noise, lens, spec.coreg_vecs,
-                     spec.coreg_diags, rep)
+                     spec.coreg_diags, rep, slfm_identity)
     op.dists = dists
     return op
 
@@ -468,8 +497,12 @@ def build_operator(spec, Xs, grids, rep='auto'):
 # reference wrapper runlmc/approx/iterative.py:24-62
 # ---------------------------------------------------------------------------
 
-def minres(matvec, b, rtol, maxiter, callback=None, trace_at=()):
+def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None):
     """Paige-Saunders MINRES, arithmetic order as scipy's.
+
+    ``psolve``: the preconditioner M (an SPD approximation of the INVERSE, scipy's ``M``:
+    ``y = psolve(r)``, minres.py:256 and :313), None = identity.  istop = 9 stands for scipy's
+    ValueError on an indefinite preconditioner (r . M r < 0).
 
     Returns (x, istop, itn, trace) where trace maps iteration -> copy of x for
     the iterations listed in ``trace_at``."""
@@ -478,8 +511,10 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=()):
     x = np.zeros(n)
     trace = {}
     r1 = b.copy()
-    y = r1
+    y = r1 if psolve is None else psolve(r1)
     beta1 = np.inner(r1, y)
+    if beta1 < 0:
+        return x, 9, 0, trace
     if beta1 == 0:
         return x, 0, 0, trace
     beta1 = math.sqrt(beta1)
@@ -511,8 +546,12 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=()):
         y = y - (alfa / beta) * r2
         r1 = r2
         r2 = y
+        if psolve is not None:
+            y = psolve(r2)
         oldb = beta
         beta = np.inner(r2, y)
+        if beta < 0:
+            return x, 9, itn, trace
         beta = math.sqrt(beta)
         tnorm2 += alfa ** 2 + oldb ** 2 + beta ** 2
         if itn == 1 and beta / beta1 <= 10 * EPS:
@@ -610,14 +649,15 @@ class _Early(Exception):
         self.x = x
 
 
-def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100, use_minres=True):
+def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100, use_minres=True, psolve=None):
     """Iterative.solve with verbose=True (minres=True unless ``use_minres`` is false: then scipy's cg
     restated above runs behind the same wrapper); iterative.py:24-62.
 
     rtol = min(1e-10, tol), maxiter = n, and on every 100th callback the true
     residual ||y - Kx||_2 is formed; < tol terminates (iterative.py:36-42).
     Returns (x, callbacks, final abs residual).  ``use_scipy`` swaps the
-    restated loop for scipy's own minres (same result; used to pin the loop)."""
+    restated loop for scipy's own minres (same result; used to pin the loop).
+    ``psolve``: K.preconditioner, forwarded as scipy's M (iterative.py:47-50; MINRES only)."""
     y = np.asarray(y, dtype=float)
     n = len(y)
     ctr = 0
@@ -635,9 +675,11 @@ def iterative_solve(matvec, y, tol=1e-4, use_scipy=False, check_every=100, use_m
             op = scipy.sparse.linalg.LinearOperator(
                 (n, n), matvec=matvec, dtype=np.float64)
             method = scipy.sparse.linalg.minres if use_minres else scipy.sparse.linalg.cg
-            x, _ = method(op, y, rtol=rtol, maxiter=n, callback=cb)
+            M = None if psolve is None else scipy.sparse.linalg.LinearOperator(
+                (n, n), matvec=psolve, dtype=np.float64)
+            x, _ = method(op, y, rtol=rtol, maxiter=n, M=M, callback=cb)
         elif use_minres:
-            x, _, _, _ = minres(matvec, y, rtol, n, callback=cb)
+            x, _, _, _ = minres(matvec, y, rtol, n, callback=cb, psolve=psolve)
         else:
             x, _, _ = cg(matvec, y, rtol, n, callback=cb)
     except _Early as e:

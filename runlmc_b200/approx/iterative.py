@@ -73,11 +73,17 @@ class Iterative:
             raise NotImplementedError('preconditioned solves are not part of the accelerated path')
         y = np.asarray(y, dtype=np.float64)
         X, iters, resid, istop = solve_block(K, y.reshape(1, -1), tol=tol, minres=minres)
-        n = K.shape[0]
-        exhausted = istop[0] == 6 if minres else istop[0] not in (0, 10)
-        if resid[0] > tol or exhausted:
-            _LOG.critical('MINRES (n = %d) did not converge in n iterations.'
-                          ' Reconstruction error %e', n, resid[0])
+        Iterative.report(K, resid, istop, tol, minres)
         if verbose:
             return X[0], int(iters[0]), float(resid[0])
         return X[0]
+
+    @staticmethod
+    def report(K, resid, istop, tol, minres=True):
+        """The reference never raises on non-convergence, it logs (iterative.py:55-58)."""
+        n = K.shape[0]
+        for r, st in zip(resid, istop):
+            exhausted = st == 6 if minres else st not in (0, 10)
+            if r > tol or exhausted:
+                _LOG.critical('MINRES (n = %d) did not converge in n iterations.'
+                              ' Reconstruction error %e', n, r)

@@ -25,10 +25,11 @@ int op_set_params_dev(lmc_op* op, int Q, const double* top_dev, const double* B_
     const long bins = op->emb.bins, cells = op->emb.cells;
     const int D = op->D;
     if (Q > op->spec_cap) {
-        cudaFree(op->spec); cudaFree(op->B); cudaFree(op->specL);
-        op->spec = nullptr; op->B = nullptr; op->specL = nullptr; op->spec_cap = 0;
+        cudaFree(op->spec); cudaFree(op->B); cudaFree(op->specL); cudaFree(op->specP);
+        op->spec = nullptr; op->B = nullptr; op->specL = nullptr; op->specP = nullptr; op->spec_cap = 0;
         LMC_CHECK(cudaMalloc(&op->spec, sizeof(double) * (size_t)Q * bins));
         LMC_CHECK(cudaMalloc(&op->specL, sizeof(double) * (size_t)Q * bins));
+        if (op->eng.col512()) LMC_CHECK(cudaMalloc(&op->specP, sizeof(double) * (size_t)Q * bins));
         LMC_CHECK(cudaMalloc(&op->B, sizeof(double) * (size_t)Q * D * D));
         op->spec_cap = Q;
     }
@@ -41,7 +42,7 @@ int op_set_params_dev(lmc_op* op, int Q, const double* top_dev, const double* B_
     for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q)
         rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
     op->fused = op->eng.fused_supported(D, Q) && getenv("LMC_NO_FUSED") == nullptr;
-    if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, Q, 0);
+    if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, op->specP, Q, 0);
     if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
     cudaFree(work);
     if (rc != 0) return rc;

@@ -79,7 +79,7 @@ int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st) {
         const int qc = std::min(step, cnt - q0);
         cplx* g = G + (size_t)q0 * slab;
         if (op->fused)
-            LMC_TRY(op->eng.apply_fused(g, op->S, qc, op->D, op->Q, op->specL, op->mix_spec(), st));
+            LMC_TRY(op->eng.apply_fused(g, op->S, qc, op->D, op->Q, op->specL, op->specP, op->mix_spec(), st));
         else
             LMC_TRY(op_grid_apply(op, g, qc, op->Q, op->spec, op->B, st));
     }
@@ -147,6 +147,7 @@ lmc_op::~lmc_op() {
         if (hs[i]) cudaStreamDestroy(hs[i]);
     cudaFree(spec);
     cudaFree(specL);
+    cudaFree(specP);
     cudaFree(B);
     cudaFree(noise);
     cudaFree(G);

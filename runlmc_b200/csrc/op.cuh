@@ -12,6 +12,7 @@ struct lmc_op {
     lmc::PointSet ps;
     double* spec = nullptr;   // [Q][bins] real circulant spectra / bins (digit-reversed layout)
     double* specL = nullptr;  // [Q][line][pos] line-major copy for the fused spectral kernel
+    double* specP = nullptr;  // same in the mix layout of the 512-point column kernel (when used)
     double origin[2] = {0.0, 0.0}, delta[2] = {1.0, 1.0};   // grid axes: origin + k * delta
     std::vector<double> B_host;
     // kernel descriptors of the last lmc_op_set_kernels (empty after lmc_op_set_params): kinds[Q],

@@ -529,6 +529,7 @@ SpectralEngine::~SpectralEngine() {
         if (tw_[p]) cudaFree(tw_[p]);
     if (stage_tw_) cudaFree(stage_tw_);
     if (stage_tw_rows_) cudaFree(stage_tw_rows_);
+    if (tw512_) cudaFree(tw512_);
 }
 
 int SpectralEngine::init(const Embedding& emb) {
@@ -750,7 +751,7 @@ size_t SpectralEngine::fused_elems_per_pair(int D) const {
     return 0;   // 1-D short lines are transformed in place in the grid slabs
 }
 
-int SpectralEngine::spectrum_lines(const double* spec, double* specL, int Q, cudaStream_t st) {
+int SpectralEngine::spectrum_lines(const double* spec, double* specL, double* specP, int Q, cudaStream_t st) {
     for (int q = 0; q < Q; ++q) {
         const double* in = spec + (size_t)q * emb_.bins;
         double* out = specL + (size_t)q * emb_.bins;
@@ -763,16 +764,29 @@ int SpectralEngine::spectrum_lines(const double* spec, double* specL, int Q, cud
             LMC_CHECK(cudaMemcpyAsync(out, in, sizeof(double) * emb_.bins, cudaMemcpyDeviceToDevice, st));
         }
     }
+    if (specP && col512()) {
+        if (!tw512_) {
+            LMC_CHECK(cudaMalloc(&tw512_, sizeof(cplx) * kC512Tw));
+            col512_twiddle_kernel<<<ceil_div(kC512Tw, 128), 128, 0, st>>>(tw512_);
+            count_launch();
+        }
+        const long total = (long)Q * emb_.bins;
+        col512_spec_kernel<<<ceil_div(total, 256), 256, 0, st>>>(specL, specP, total);
+        count_launch();
+        LMC_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 
 int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL,
-                                const MixSpec& mix, cudaStream_t st) {
+                                const double* specP, const MixSpec& mix, cudaStream_t st) {
     if (npairs == 0) return 0;
     const Embedding& e = emb_;
     FusedArgs f = {};
     f.Q = Q;
     f.specL = specL;
+    f.specP = col512() ? specP : nullptr;
+    f.tw512 = tw512_;
     // stage twiddle table of the fused kernel's line length (built on first use)
     const int Lf = e.ndim == 2 ? e.mt[0] : e.L2;
     if (!stage_tw_) {

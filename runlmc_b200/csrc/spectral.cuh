@@ -59,9 +59,12 @@ class SpectralEngine {
     // elements of scratch S needed per RHS pair on the fused path
     size_t fused_elems_per_pair(int D) const;
     // line-major spectra for the fused kernel: specL[q][line][pos]  (2-D: transposed copy of spec)
-    int spectrum_lines(const double* spec, double* specL, int Q, cudaStream_t st);
-    int apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL, const MixSpec& mix,
-                    cudaStream_t st);
+    // specP (same size, may be null): the copy in the mix layout of the 512-point column kernel
+    // (spectral_col512.cuh), filled when the geometry uses it
+    int spectrum_lines(const double* spec, double* specL, double* specP, int Q, cudaStream_t st);
+    bool col512() const { return emb_.ndim == 2 && emb_.mt[0] == 512; }
+    int apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, const double* specL, const double* specP,
+                    const MixSpec& mix, cudaStream_t st);
 
   private:
     Embedding emb_;
@@ -71,6 +74,7 @@ class SpectralEngine {
     FftPlan plan1_, plan2_;                       // four-step sub-plans
     cplx* stage_tw_rows_ = nullptr;               // same for the transposing row pass (2-D)
     cplx* stage_tw_ = nullptr;                    // per-stage twiddles of the fused kernel's line length
+    cplx* tw512_ = nullptr;                       // first-stage twiddles of the 512-point column kernel
 };
 
 // real grid vectors X[k][D*m] <-> complex pair slabs Z[ceil(k/2)][D][gpitch]

@@ -4,8 +4,10 @@
 #pragma once
 #include "spectral.cuh"
 #include "fft.cuh"
+#include "spectral_col512.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace lmc {
 
@@ -111,6 +113,8 @@ struct FusedArgs {
     StageTw lay;
     FftPlan plan;
     int pitch, half;
+    const double* specP;          // spectra in the col512 mix layout (or null)
+    const cplx* tw512;            // col512 first-stage twiddles
 };
 
 template <int D, class MIX>
@@ -162,9 +166,35 @@ __global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, 
 }
 
 
+// the register/shuffle column kernel for 512-point pruned lines (spectral_col512.cuh)
+static inline bool use_col512(const FusedArgs& a) {
+    static const bool off = getenv("LMC_NO_COL512") != nullptr;
+    return !off && a.L == 512 && a.half && a.specP && a.tw512 && a.valid <= 256;
+}
+
+template <int D, class MIX>
+static int launch_col512_kernel(const FusedArgs& a, const MIX& m, int npairs, cudaStream_t st) {
+    static const int ppc_env = getenv("LMC_COL512_PPC") ? atoi(getenv("LMC_COL512_PPC")) : 1;
+    const size_t smem = sizeof(cplx) * (size_t)(kC512Tw + D * kC512Line);
+    static bool attr = false;
+    if (!attr) {
+        LMC_CHECK(cudaFuncSetAttribute(fused_col512_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kFusedSmemMax));
+        attr = true;
+    }
+    Col512Args c = {};
+    c.data = a.data; c.slab_stride = a.slab_stride; c.line_stride = a.line_stride;
+    c.n_lines = a.n_lines; c.valid = a.valid; c.npairs = npairs; c.ppc = std::max(1, ppc_env);
+    c.Q = a.Q; c.specP = a.specP; c.tw1 = a.tw512;
+    dim3 grid((unsigned)a.n_lines, (unsigned)ceil_div(npairs, c.ppc));
+    fused_col512_kernel<D, MIX><<<grid, 32 * D, smem, st>>>(c, m);
+    return 0;
+}
+
 template <int D, class MIX>
 static int launch_fused_kernel(const FusedArgs& a, const MIX& m, dim3 grid, int threads, size_t smem,
                                cudaStream_t st) {
+    if (use_col512(a)) return launch_col512_kernel<D, MIX>(a, m, (int)grid.y, st);
     static bool attr = false;
     if (!attr) {
         LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,

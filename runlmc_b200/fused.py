@@ -120,6 +120,10 @@ class FusedLMC:
         desc = [kernel_descriptor(k) for k in kerns]
         if any(d is None for d in desc):
             raise ValueError('only RBF, Matern32 and StdPeriodic kernels are evaluated on the device')
+        self.set_kernel_descriptors(desc, Bs, noise, coreg_vecs, coreg_diags)
+
+    def set_kernel_descriptors(self, desc, Bs, noise, coreg_vecs=None, coreg_diags=None):
+        """set_kernels from (kind, inv_lengthscale, period) triples (kernel_descriptor)."""
         kinds = nat.as_i32([d[0] for d in desc])
         params = nat.as_f64([[d[1], d[2]] for d in desc])
         Bs = nat.as_f64(np.array(Bs))

@@ -5,8 +5,11 @@
 a device-backed runlmc_b200.linalg class -- and, when the tree is the standard
 single-active-dimension-group SKI-LMC operator, attaches ONE fused CUDA
 operator (`_fused`) that `matvec`, `Iterative.solve` and the likelihood use
-instead of walking the tree.  sum / bt / slfm are the same matrix; the fused
-operator serves all three."""
+instead of walking the tree.  sum / bt / slfm are the same matrix (except the
+reference's slfm tree with an empty coreg or diag part, which is left to the
+tree, see _try_fuse); the fused operator serves all three.  The handle is shared
+by the operators built from one interpolant, each of which re-binds its own
+hyper-parameters before use (_ParamState)."""
 import numpy as np
 
 from ..approx.ski import SKI
@@ -24,38 +27,126 @@ from ..fused import FusedLMC, kernel_descriptor
 
 
 class GridKernel(Matrix):
+    """One active-dimension group of the SKI-LMC operator in the reference's representation `ktype`
+    (grid_kernel.py:22-41).  `grid_K` / `ski` are assembled on first access from a snapshot of the
+    hyper-parameters taken here: when the fused operator serves the products (the usual case) the
+    O(Q m) host kernel evaluation and the tree of up to D^2 BTTB nodes are never built."""
+
     def __init__(self, functional_kernel, grid_dists, interpolant, interpolantT, ktype, active_dim):
         n = interpolant.shape[0]
         super().__init__(n, n)
-        grid_k = functional_kernel.eval_kernels_fixed_dim(grid_dists, active_dim)
-        if ktype == 'sum':
-            self.grid_K = _gen_sum_grid(functional_kernel, grid_k, active_dim)
-        elif ktype == 'bt':
-            self.grid_K = _gen_bt_grid(functional_kernel, grid_k, active_dim)
-        elif ktype == 'slfm':
-            self.grid_K = _gen_slfm_grid(functional_kernel, grid_k, interpolant.shape[1], active_dim)
-        else:
-            assert False, ktype
+        assert ktype in ('sum', 'bt', 'slfm'), ktype
         self.ktype = ktype
-        self.ski = SKI(self.grid_K, interpolant, interpolantT)
+        self._interp = (interpolant, interpolantT)
+        self._build = (_FrozenKernel(functional_kernel, active_dim, grid_dists), grid_dists, active_dim)
+        self._grid_K = self._ski = None
+
+    @property
+    def grid_K(self):
+        if self._grid_K is None:
+            fk, grid_dists, active_dim = self._build
+            grid_k = fk.eval_kernels_fixed_dim(grid_dists, active_dim)
+            if self.ktype == 'sum':
+                self._grid_K = _gen_sum_grid(fk, grid_k, active_dim)
+            elif self.ktype == 'bt':
+                self._grid_K = _gen_bt_grid(fk, grid_k, active_dim)
+            else:
+                self._grid_K = _gen_slfm_grid(fk, grid_k, self._interp[0].shape[1], active_dim)
+        return self._grid_K
+
+    @property
+    def ski(self):
+        if self._ski is None:
+            self._ski = SKI(self.grid_K, *self._interp)
+        return self._ski
 
     def _apply_dev(self, X):
         return self.ski._apply_dev(X)
 
 
+class _FrozenKernel:
+    """What a GridKernel needs of a FunctionalKernel for one active-dimension group, with the
+    hyper-parameters copied at construction (the optimiser updates the FunctionalKernel in place,
+    an operator built earlier must keep its own values like the reference's does)."""
+
+    def __init__(self, fk, active_dim, grid_dists):
+        import copy
+        idxs = list(fk.active_dims[active_dim])
+        self.D, self.Q = fk.D, fk.Q
+        self.active_dims = {active_dim: idxs}
+        self.coreg_vecs = [np.array(a, dtype=float) for a in fk.coreg_vecs]
+        self.coreg_diags = [np.array(k, dtype=float) for k in fk.coreg_diags]
+        self.num_lmc = {active_dim: fk.num_lmc[active_dim]}
+        self.num_indep = {active_dim: fk.num_indep[active_dim]}
+        self._non_indep = list(fk.filter_non_indep_idxs(idxs))
+        kernels = getattr(fk, '_kernels', None)
+        self._kernels = copy.deepcopy(kernels) if kernels is not None else None
+        # duck-typed stand-ins without kernel objects cannot be snapshotted: evaluate them now
+        self._grid_k = None if kernels is not None else fk.eval_kernels_fixed_dim(grid_dists, active_dim)
+
+    def eval_kernels_fixed_dim(self, dists, active_dim):
+        if self._kernels is not None:
+            return np.array([self._kernels[k].from_dist(dists) for k in self.active_dims[active_dim]])
+        return self._grid_k
+
+    def coreg_mats(self, active_dim=None):
+        idxs = range(len(self.coreg_vecs)) if active_dim is None else self.active_dims[active_dim]
+        return [self.coreg_vecs[i].T.dot(self.coreg_vecs[i]) + np.diag(self.coreg_diags[i]) for i in idxs]
+
+    def filter_non_indep_idxs(self, idxs):
+        return [k for k in idxs if k in self._non_indep]
+
+
+class _ParamState:
+    """The hyper-parameters of ONE gen_grid_kernel call, as the fused handle takes them.  The handle
+    (point sort, workspace) is shared by every operator built from the same interpolant; `bind` makes
+    it hold THIS operator's parameters before it is used, so operators built earlier keep their own
+    values (K(theta + h) and K(theta - h) side by side, a prediction operator held across optimiser
+    steps) -- like the reference, whose gen_grid_kernel returns independent operators."""
+
+    def __init__(self, descs, tops, Bs, noise, coreg_vecs, coreg_diags):
+        self.descs = descs
+        self.tops = None if tops is None else [np.array(t, dtype=float) for t in tops]
+        self.Bs = [np.array(B, dtype=float) for B in Bs]
+        self.noise = np.array(noise, dtype=float)
+        self.coreg_vecs = [np.array(a, dtype=float) for a in coreg_vecs]
+        self.coreg_diags = [np.array(k, dtype=float) for k in coreg_diags]
+
+    def bind(self, fused):
+        if getattr(fused, '_bound_state', None) is not self:
+            if self.descs is not None:
+                fused.set_kernel_descriptors(self.descs, self.Bs, self.noise, self.coreg_vecs, self.coreg_diags)
+            else:
+                fused.set_params(self.tops, self.Bs, self.noise, self.coreg_vecs, self.coreg_diags)
+            fused._bound_state = self
+        return fused
+
+
 class FusedSumMatrix(SumMatrix):
     """SumMatrix([GridKernel, Diag(noise)]) collapsed into one device handle."""
 
-    def __init__(self, Ks, fused):
+    def __init__(self, Ks, fused, state=None):
         super().__init__(Ks)
-        self._fused = fused
+        self._handle = fused
+        self._state = state
+
+    @property
+    def _fused(self):
+        """The device operator holding this matrix's hyper-parameters (None after unpickling)."""
+        if self._handle is None:
+            return None
+        return self._state.bind(self._handle) if self._state is not None else self._handle
 
     def _apply_dev(self, X):
-        return self._fused.mvm_device(X.contiguous())
+        fused = self._fused
+        if fused is None:           # unpickled: walk the (device-backed) tree like any SumMatrix
+            return super()._apply_dev(X)
+        return fused.mvm_device(X.contiguous())
 
     def __getstate__(self):
         state = super().__getstate__()
-        state['_fused'] = None      # device handles are not picklable
+        state['_handle'] = None      # device handles are not picklable
+        state['_state'] = None
         return state
 
 
@@ -79,13 +170,15 @@ def gen_grid_kernel(fk, grid_dists, interpolants, lens_per_output):
     ls.append(noise)
     fused = _try_fuse(fk, grid_dists, interpolants, lens_per_output)
     if fused is not None:
-        return FusedSumMatrix(ls, fused), grid_kerns
+        handle, state = fused
+        state.bind(handle)
+        return FusedSumMatrix(ls, handle, state), grid_kerns
     return SumMatrix(ls), grid_kerns
 
 
 def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
-    """One fused operator when there is a single active-dimension group of 1 or 2
-    input dimensions and the interpolant carries its geometry."""
+    """(handle, parameter state) of one fused operator when there is a single active-dimension group
+    of 1 or 2 input dimensions and the interpolant carries its geometry, else None."""
     if len(fk.active_dims) != 1:
         return None
     (active_dim,) = fk.active_dims.keys()
@@ -93,22 +186,30 @@ def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
     geom = getattr(W, 'lmc_geometry', None)
     if geom is None or len(geom[1]) not in (1, 2) or fk.D > 16:
         return None
+    idxs = fk.active_dims[active_dim]
+    if representation(fk, active_dim) == 'slfm' and (
+            not fk.filter_non_indep_idxs(idxs) or
+            (fk.num_lmc[active_dim] == 0 and fk.num_indep[active_dim] == 0)):
+        # the reference's slfm tree puts Identity(m) in place of an empty coreg or diag part
+        # (grid_kernel.py:84-86, 101-103): that operator is W (sum_q B_q x T_q + I) W^T + noise, which
+        # the fused handle does not represent -- leave it to the tree, which reproduces it
+        return None
     Xs, grids = geom
     cache = getattr(W, '_lmc_fused', None)
     if cache is None:
         cache = FusedLMC(Xs, grids)          # X-dependent sort happens once per model
         W._lmc_fused = cache
-    idxs = fk.active_dims[active_dim]
-    factors = dict(coreg_vecs=[fk.coreg_vecs[i] for i in idxs],
-                   coreg_diags=[fk.coreg_diags[i] for i in idxs])
+    coreg_vecs = [fk.coreg_vecs[i] for i in idxs]
+    coreg_diags = [fk.coreg_diags[i] for i in idxs]
     kerns = _device_kernels(fk, idxs, cache, grid_dists[active_dim])
     if kerns is not None:
         # per-step setup on the device: kernel values are evaluated where the spectra are computed
-        cache.set_kernels(kerns, fk.coreg_mats(active_dim), fk.noise, **factors)
+        state = _ParamState([kernel_descriptor(k) for k in kerns], None, fk.coreg_mats(active_dim), fk.noise,
+                            coreg_vecs, coreg_diags)
     else:
         grid_k = fk.eval_kernels_fixed_dim(grid_dists[active_dim], active_dim)
-        cache.set_params(list(grid_k), fk.coreg_mats(active_dim), fk.noise, **factors)
-    return cache
+        state = _ParamState(None, list(grid_k), fk.coreg_mats(active_dim), fk.noise, coreg_vecs, coreg_diags)
+    return cache, state
 
 
 def _device_kernels(fk, idxs, fused, dists):

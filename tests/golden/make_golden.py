@@ -315,7 +315,71 @@ class _ListKey(list):
         return hash(tuple(self))
 
 
+class DuckKindKernel(DuckKernel):
+    """Stand-in whose kernels are all SLFM-type (rank-1 coregionalisation, no diagonal) or all
+    independent GPs (no coregionalisation vectors, diagonal e_d): the cases in which the reference's
+    slfm representation substitutes Identity(m) for the empty part (grid_kernel.py:84-86, 101-103)."""
+
+    def __init__(self, prob, kind):
+        super().__init__(prob)
+        Q, D = prob.Q, prob.D
+        self.kind = kind
+        if kind == 'slfm':
+            self.coreg_diags = [np.zeros(D) for _ in range(Q)]
+            self.num_lmc, self.num_slfm = {self.ad: 0}, {self.ad: Q}
+        else:
+            self.coreg_vecs = [np.zeros((1, D)) for _ in range(Q)]
+            self.coreg_diags = [np.eye(D)[q % D] for q in range(Q)]
+            self.num_lmc, self.num_indep = {self.ad: 0}, {self.ad: Q}
+
+    def coreg_mats(self, active_dim=None):
+        return [a.T.dot(a) + np.diag(k) for a, k in zip(self.coreg_vecs, self.coreg_diags)]
+
+    def total_rank(self, active_dim):
+        return 0 if self.kind == 'indep' else sum(len(a) for a in self.coreg_vecs)
+
+    def filter_non_indep_idxs(self, idxs):
+        return [] if self.kind == 'indep' else list(idxs)
+
+
+def main_extra():
+    """(1) gen_grid_kernel for SLFM-only and independent-GP-only kernels; (2) Iterative.solve with a
+    K.preconditioner (forwarded to scipy as M, iterative.py:47-50): the Jacobi preconditioner
+    Diag(1 / diag(K)) with the diagonal taken from the reference's own dense K."""
+    out = {}
+    prob = synthetic.make_problem('e_small', seed=99, cells_per_lengthscale=3, lens=[120, 90, 100],
+                                  grid=[12, 10], N=5)
+    W = ref_interp.multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    rs = np.random.RandomState(3)
+    V = rs.randn(3, prob.n)
+    out['V'] = V
+    for kind in ('slfm', 'indep'):
+        fk = DuckKindKernel(prob, kind)
+        K, kerns = gen_grid_kernel(fk, {fk.ad: prob.dists}, {fk.ad: (W, WT)}, prob.lens)
+        ktype = {'SumMatrix': 'slfm-or-sum', 'SymmSquareBlockMatrix': 'bt'}[type(kerns[fk.ad].grid_K).__name__]
+        parts = [type(k).__name__ for k in kerns[fk.ad].grid_K.Ks]
+        out[kind + '_parts'] = np.array(parts)
+        out[kind + '_KV'] = np.array([K.matvec(v) for v in V])
+        out[kind + '_coreg_vecs'] = np.array(fk.coreg_vecs)
+        out[kind + '_coreg_diags'] = np.array(fk.coreg_diags)
+        print(kind, 'representation', ktype, parts)
+    for name, p in (('2d', prob), ('A', synthetic.make_problem('A', seed=1234, edge=True, cells_per_lengthscale=4))):
+        fk = DuckKernel(p)
+        Wp = ref_interp.multi_interpolant(p.Xs, *p.grids)
+        K, _ = gen_grid_kernel(fk, {fk.ad: p.dists}, {fk.ad: (Wp, Wp.transpose().tocsr())}, p.lens)
+        dK = np.diag(K.as_numpy()).copy()
+        K.preconditioner = Diag(1.0 / dK)
+        x, ctr, err = Iterative.solve(K, p.y, verbose=True, minres=True, tol=1e-4)
+        out['pre_%s_diag' % name], out['pre_%s_x' % name] = dK, x
+        out['pre_%s_ctr' % name], out['pre_%s_err' % name] = np.array(ctr), np.array(err)
+        print('preconditioned', name, 'callbacks', ctr, 'residual', err)
+    np.savez_compressed(os.path.join(HERE, 'extra.npz'), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'extra':
+        return main_extra()
     if len(sys.argv) > 1 and sys.argv[1] == 'predict':
         return main_predict()
     if len(sys.argv) > 1 and sys.argv[1] == 'cg':

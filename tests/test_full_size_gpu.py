@@ -1,17 +1,97 @@
-"""Properties of the CUDA path at BASELINE.json's full sizes (config D: n = 500k, 1-D grid 8192;
-config E: n = 1M, 2-D grid 256 x 256), where the oracle would take minutes per product: linearity,
-symmetry, adjointness of the two interpolation stages, agreement of wide blocks with single columns
-and of the sorted-order entry point with the caller-order one, and the solver's reported residual
-against a residual formed from a separate product."""
+"""The CUDA path at BASELINE.json's full sizes (config B: n = 10k, 1-D grid 1024; config D: n = 500k,
+1-D grid 8192; config E: n = 1M, 2-D grid 256 x 256, D = 10 -- the 512-point fused column kernel the
+headline number is measured on).
+
+1. Oracle parity at the stated sizes: the product, its three stages and the first MINRES iterates
+   against the numpy/scipy oracle on identical inputs (the oracle builds E's 16 M-nnz interpolation
+   matrix in a few seconds and takes ~0.25 s per product), <= 1e-10 relative per column.
+2. Size-independent properties on full-width blocks: linearity, symmetry, adjointness of the two
+   interpolation stages, agreement of wide blocks with single columns and of the sorted-order entry
+   point with the caller-order one, and the solver's reported residual against a residual formed
+   from a separate product."""
 import numpy as np
 import pytest
 
 from conftest import rel_err
+from oracle import lmc_oracle as orc
 from runlmc_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
-CPL = {'D': 2, 'E': 1.5}     # bench.py's lengthscales for these workloads
+CPL = {'B': 8, 'D': 2, 'E': 1.5}     # bench.py's lengthscales for these workloads
+WIDTH = {'B': 17, 'D': 65, 'E': 129}  # y + the config's probes
+MVM_TOL = 1e-10                       # north_star: MVMs within 1e-10 relative
+
+
+@pytest.fixture(scope='module', params=['B', 'D', 'E'])
+def stated(request):
+    """Operator, oracle and a full-width block of the config's own right-hand sides (y + probes)."""
+    from runlmc_b200 import kern
+    from runlmc_b200.fused import FusedLMC
+    name = request.param
+    prob = synthetic.make_problem(name, seed=1234, cells_per_lengthscale=CPL[name])
+    op = FusedLMC(prob.Xs, prob.grids)
+    op.set_kernels([kern.RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
+                   prob.coreg_diags)
+    spec = orc.KernelSpec(['rbf'] * prob.Q, [[g] for g in prob.gammas], prob.coreg_vecs,
+                          prob.coreg_diags, prob.noise)
+    ref = orc.build_operator(spec, prob.Xs, prob.grids, rep='sum')
+    V = np.ascontiguousarray(np.vstack([prob.y[None, :], prob.probes]))
+    assert V.shape[0] == WIDTH[name]
+    return name, prob, op, ref, V
+
+
+def test_stated_size_product_matches_oracle(stated):
+    """Full-width block through the caller-order and the sorted-order entry points; the first pair,
+    a middle column and the odd last column against the oracle."""
+    import torch
+    name, prob, op, ref, V = stated
+    Vd = torch.as_tensor(V, device='cuda')
+    KV = op.mvm_device(Vd)
+    perm = torch.as_tensor(op.perm().astype(np.int64), device='cuda')
+    KVs = op.mvm_sorted_device(Vd[:, perm].contiguous())
+    cols = [0, 1, V.shape[0] // 2, V.shape[0] - 1]
+    for c in cols:
+        want = ref.matvec(V[c])
+        assert rel_err(KV[c].cpu().numpy(), want) < MVM_TOL
+        assert rel_err(KVs[c].cpu().numpy(), want[op.perm()]) < MVM_TOL
+    # the host-buffer entry point (chunked copy/compute pipeline) on the same block
+    got = op.mvm(V[[0, 1, V.shape[0] - 1]])
+    for g, c in zip(got, (0, 1, V.shape[0] - 1)):
+        assert rel_err(g, ref.matvec(V[c])) < MVM_TOL
+
+
+def test_stated_size_stages_match_oracle(stated):
+    import torch
+    name, prob, op, ref, V = stated
+    rng = np.random.default_rng(17)
+    v = V[[0, 1, V.shape[0] - 1]]
+    g = rng.standard_normal((3, prob.D * ref.m))
+    vd, gd = torch.as_tensor(v, device='cuda'), torch.as_tensor(g, device='cuda')
+    got = op.to_grid_device(vd).cpu().numpy()
+    for a, b in zip(got, v):
+        assert rel_err(a, ref.WT.dot(b)) < 1e-12
+    got = op.from_grid_device(gd).cpu().numpy()
+    for a, b in zip(got, g):
+        assert rel_err(a, ref.W.dot(b)) < 1e-12
+    got = op.grid_mvm_device(gd).cpu().numpy()
+    for a, b in zip(got, g):
+        assert rel_err(a, ref.grid_matvec(b)) < 1e-11
+
+
+def test_stated_size_minres_iterates_match_oracle(stated):
+    """k = 1, 3, 7 iterations of the block solver on the full-width block against the oracle's restated
+    scipy loop on the first pair and the odd last column."""
+    import torch
+    name, prob, op, ref, V = stated
+    Vd = torch.as_tensor(V, device='cuda')
+    cols = (0, 1, V.shape[0] - 1)
+    for k in (1, 3, 7):
+        X, iters, _, _ = op.minres_device(Vd, tol=1e-4, maxiter=k, check_every=10 ** 6)
+        for c in cols:
+            xr, _, itn_r, _ = orc.minres(ref.matvec, V[c], 1e-10, k)
+            assert iters[c] == itn_r
+            assert rel_err(X[c].cpu().numpy(), xr) < 1e-9
 
 
 @pytest.fixture(scope='module', params=['D', 'E'])

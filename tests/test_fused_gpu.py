@@ -43,6 +43,12 @@ PROBLEMS = {
     'ragged': lambda: synthetic.make_problem('d_small', seed=12, cells_per_lengthscale=6,
                                              lens=[1, 350, 0, 77], grid=[100], N=3),
     'C': lambda: synthetic.make_problem('C', seed=13, cells_per_lengthscale=5),
+    # 128 < m_x <= 256: the register/shuffle 512-point column kernel (spectral_col512.cuh), m_x not a
+    # multiple of 32 so the last loads/stores of a line are partially masked
+    'col512': lambda: synthetic.make_problem('e_small', seed=15, cells_per_lengthscale=4,
+                                             lens=[900, 800, 850], grid=[200, 12], N=6),
+    'col512_edge': lambda: synthetic.make_problem('e_small', seed=16, cells_per_lengthscale=4, edge=True,
+                                                  lens=[400, 0, 300, 500, 20], D=5, grid=[131, 9], N=4),
     'four_step': lambda: synthetic.make_problem('d_small', seed=14, cells_per_lengthscale=40,
                                                 lens=[3000, 2500], D=2, grid=[5000], Q=2, N=3),
 }
@@ -99,7 +105,7 @@ def test_mvm_against_reference_golden(name):
         assert rel_err(a, b) < MVM_TOL
 
 
-@pytest.mark.parametrize('name', ['2d_small', 'd_small', 'C', 'four_step'])
+@pytest.mark.parametrize('name', ['2d_small', 'd_small', 'C', 'four_step', 'col512', 'col512_edge'])
 def test_lowrank_mix_equals_dense_mix(name):
     prob = PROBLEMS[name]()
     rng = np.random.default_rng(3)
