@@ -39,39 +39,59 @@ from runlmc_b200 import synthetic  # noqa: E402
 METRIC = 'ski_lmc_mvm_rhs_per_s'
 UNIT = 'MVM*RHS/s'
 CPL = {'A': 4, 'B': 8, 'C': 5, 'D': 2, 'E': 1.5}     # grid cells per (shortest) lengthscale
+# hyper-parameters of the headline gradient row: kernels resolved by the grid and a noise level on which the
+# reference's stopping rule converges below tol (picked with tools/conv_probe.py)
+GRAD_PARAMS = {'E': dict(cpl=4.0, eps=1.0), 'D': dict(cpl=4.0, eps=1.0)}
 
 
 def workload_desc(name, prob):
+    """Identical in both arms (the driver compares `config` between them)."""
     return {'workload': '%s: D=%d n=%d grid=%s Q=%d probes=%d (SURVEY.md sec.8 config %s)' % (
         name, prob.D, prob.n, 'x'.join(map(str, prob.grid_sizes)), prob.Q, prob.N, name),
-        'rhs_per_step': prob.N + 1, 'timing': 'CUDA events; inputs (%.2f GB) larger than L2' % (
-            (prob.N + 1) * prob.n * 8 / 1e9)}
+        'rhs_per_step': prob.N + 1,
+        'cache': 'inputs of a step (%.2f GB) are larger than the 126 MB L2' % ((prob.N + 1) * prob.n * 8 / 1e9)}
 
 
 # --------------------------------------------------------------------------
 # CPU side (oracle port of the reference path)
 # --------------------------------------------------------------------------
 _CPU_OP = None
+_CPU_K = 0
 
 
 def _cpu_mvm(v):
     return _CPU_OP.matvec(v)
 
 
-def cpu_reference_rate(prob, steps, warmup, cores=None, budget_s=25.0):
-    """MVM/s of the oracle (= the reference's numpy/scipy arithmetic) with one
-    worker process per core, each step a block of `cores` columns."""
-    global _CPU_OP
-    import multiprocessing as mp
+def _cpu_solve_capped(b):
+    """_CPU_K iterations of the reference's solver on one right-hand side (one pool task per column, like
+    pool.starmap(Iterative.solve, ...), stochastic_deriv.py:51-52)."""
     from oracle import lmc_oracle as orc
-    cores = cores or len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    orc.minres(_CPU_OP.matvec, b, 1e-10, _CPU_K)
+    return time.perf_counter() - t0
+
+
+def oracle_operator(prob):
+    from oracle import lmc_oracle as orc
     spec = orc.KernelSpec(['rbf'] * prob.Q, [[g] for g in prob.gammas], prob.coreg_vecs,
                           prob.coreg_diags, prob.noise)
+    return orc.build_operator(spec, prob.Xs, prob.grids, rep='sum')
+
+
+def cpu_reference_rate(prob, steps, warmup, cores=None, budget_s=25.0, solve_iters=0, keep=False):
+    """MVM/s of the oracle (= the reference's numpy/scipy arithmetic) with one
+    worker process per core, each step a block of `cores` columns.  solve_iters > 0 also times that
+    many MINRES iterations per column through the same pool (the reference's parallel mode)."""
+    global _CPU_OP, _CPU_K
+    import multiprocessing as mp
+    cores = cores or len(os.sched_getaffinity(0))
     t0 = time.perf_counter()
-    _CPU_OP = orc.build_operator(spec, prob.Xs, prob.grids, rep='sum')
+    _CPU_OP = oracle_operator(prob)
     t_build = time.perf_counter() - t0
     cols = [prob.probes[i % prob.N] for i in range(cores)]
     ctx = mp.get_context('fork')
+    out = {}
     with ctx.Pool(cores) as pool:
         for _ in range(warmup):
             pool.map(_cpu_mvm, cols)
@@ -83,10 +103,21 @@ def cpu_reference_rate(prob, steps, warmup, cores=None, budget_s=25.0):
             if time.perf_counter() - t0 > budget_s:
                 break
         dt = time.perf_counter() - t0
-    _CPU_OP = None
-    return {'value': cores * done / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d steps x %d columns (one per core) of the %d-column block; operator build %.1f s not timed'
-                      % (done, cores, prob.N + 1, t_build), 'ms_per_step': 1e3 * dt / done, 'steps': done}
+    if solve_iters:
+        _CPU_K = solve_iters
+        with ctx.Pool(cores) as pool:           # forked after _CPU_K is set
+            t0 = time.perf_counter()
+            pool.map(_cpu_solve_capped, cols)
+            dts = time.perf_counter() - t0
+        out['minres_iter_rhs_per_s'] = cores * solve_iters / dts
+        out['minres_sample'] = 'Pool(%d).map of %d-iteration MINRES solves, one column per core, %.1f s' % (
+            cores, solve_iters, dts)
+    if not keep:
+        _CPU_OP = None
+    out.update({'value': cores * done / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                'sample': '%d steps x %d columns (one per core) of the %d-column block; operator build %.1f s not timed'
+                          % (done, cores, prob.N + 1, t_build), 'ms_per_step': 1e3 * dt / done, 'steps': done})
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -220,6 +251,143 @@ def ncu_traffic(workload, family, pairs_per_launch):
 
 
 # --------------------------------------------------------------------------
+def rfft_bins(op):
+    """Number of rfft bins m~_c of the embedding: m~_1 ... (m~_P / 2 + 1)."""
+    mt = [1 << int(2 * m - 1).bit_length() for m in op.grid_sizes]
+    out = mt[-1] // 2 + 1
+    for v in mt[:-1]:
+        out *= v
+    return out
+
+
+def parity_check(op, ref, Vh, OUT, tol=1e-10):
+    """The timed operator's own output against the oracle on the first pair and the odd last column."""
+    cols = sorted({0, min(1, len(Vh) - 1), len(Vh) - 1})
+    errs = []
+    for c in cols:
+        want = ref.matvec(Vh[c])
+        got = OUT[c].cpu().numpy()
+        errs.append(float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+    return {'columns': cols, 'max_rel_err_vs_oracle': max(errs), 'tolerance': tol, 'ok': max(errs) <= tol,
+            'oracle': 'oracle/lmc_oracle.py (numpy/scipy restatement pinned to the reference)'}
+
+
+def timed_product(op, V, OUT, steps, warmup, barrier, min_warm_s=0.5):
+    import torch
+    t_w = time.time()
+    while True:                                   # warm-up: >= W steps and long enough for the clocks to settle
+        for _ in range(warmup):
+            op.mvm_device(V, OUT)
+        torch.cuda.synchronize()
+        if time.time() - t_w > min_warm_s:
+            break
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        op.mvm_device(V, OUT)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def gradient_row(op, prob, rank, world, dev, barrier, peak, label, note):
+    """One full stochastic gradient evaluation (solves + all partials) with the operator's current
+    hyper-parameters."""
+    import torch
+    import torch.distributed as dist
+    from runlmc_b200.distributed import sharded_gradient
+    barrier()
+    t0 = time.perf_counter()
+    grads, stats = sharded_gradient(op, prob.y, prob.probes, None, prob.coreg_vecs,
+                                    prob.coreg_mats(), tol=1e-4, rank=rank, world=world)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    flat = np.concatenate([np.ravel(g) for g in grads[0]] + [np.ravel(g) for g in grads[1]] +
+                          [np.ravel(g) for g in grads[2]] + [np.ravel(grads[3])])
+    it_rate = stats['iterations'] * (prob.N + 1) / dt
+    return {'row': label, 'note': note, 'grad_evals_per_s': 1.0 / dt, 'seconds': dt,
+            'mean_minres_iterations': stats['iterations'], 'mean_final_residual': stats['solv_error'],
+            'tol': 1e-4, 'converged': bool(stats['solv_error'] < 1e-4),
+            'hyperparameters': int(flat.size), 'minres_iter_rhs_per_s': it_rate,
+            'lengthscales_in_grid_cells': [float(1.0 / np.sqrt(g) * (max(prob.grid_sizes) - 1)) for g in prob.gammas],
+            'noise': [float(prob.noise.min()), float(prob.noise.max())],
+            'gradient_l2': float(np.linalg.norm(flat)), 'gradient_checksum': float(flat.sum()),
+            'gradient_values': [float(v) for v in flat],
+            'includes': 'host->device copies of y/probes, N+1 MINRES solves (tol 1e-4, reference stopping rules), '
+                        'all partial derivatives, allreduce',
+            # MINRES against B_minres_iter = 120 n bytes per iteration and RHS (SURVEY.md sec. 8d)
+            'roofline_minres': {'bound': 'hbm', 'alg_bytes_per_iter_rhs': 120.0 * prob.n,
+                                'achieved': 120.0 * prob.n * it_rate / world / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                'frac': 120.0 * prob.n * it_rate / world / 1e9 / peak, 'note': 'per GPU'}}
+
+
+def small_config_row(name, peak):
+    """A secondary workload on ONE GPU: block-product rate and MINRES iteration rate of the device path,
+    with the CPU port's serial MINRES iteration rate beside it (configs A/B/C are launch bound, D is the
+    HBM-bound one)."""
+    import torch
+    from oracle import lmc_oracle as orc
+    from runlmc_b200.fused import FusedLMC
+    from runlmc_b200.kern import RBF
+    from runlmc_b200 import _native as nat
+    prob = synthetic.make_problem(name, seed=1234, cells_per_lengthscale=CPL[name])
+    op = FusedLMC(prob.Xs, prob.grids)
+    op.set_kernels([RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+    Vh = np.ascontiguousarray(np.vstack([prob.y[None, :], prob.probes]))
+    P = Vh.shape[0]
+    V = torch.as_tensor(Vh, device='cuda')
+    OUT = torch.empty_like(V)
+    steps = 20 if prob.n >= 100000 else 200
+    ms = timed_product(op, V, OUT, steps, 3, torch.cuda.synchronize, min_warm_s=0.1) / steps
+    perm = torch.as_tensor(op.perm().astype(np.int64), device='cuda')
+    Vs = V[:, perm].contiguous()
+    for _ in range(3):
+        op.mvm_sorted_device(Vs, OUT)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        op.mvm_sorted_device(Vs, OUT)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_sorted = e0.elapsed_time(e1) / steps
+    bins = nat.lib.lmc_op_embed_bins(op._h)
+    b_mvm = 16.0 * prob.n * P + 8.0 * prob.ndim * prob.n + 8.0 * prob.Q * bins + 8.0 * prob.D
+    # MINRES: K iterations on the whole block (no column converges that early), launches counted
+    K = 50
+    op.minres_device(V, tol=1e-4, maxiter=5, check_every=10 ** 6)
+    torch.cuda.synchronize()
+    l0 = nat.lib.lmc_launch_count()
+    t0 = time.perf_counter()
+    _, iters, _, _ = op.minres_device(V, tol=1e-4, maxiter=K, check_every=10 ** 6)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = int(nat.lib.lmc_launch_count() - l0)
+    done = float(np.sum(iters))
+    # CPU port, serial, same iteration count on a few columns (bounded)
+    ref = oracle_operator(prob)
+    ncpu = 2 if prob.n >= 100000 else 4
+    t0 = time.perf_counter()
+    for c in range(ncpu):
+        orc.minres(ref.matvec, Vh[c], 1e-10, K)
+    dcpu = time.perf_counter() - t0
+    par = parity_check(op, ref, Vh, op.mvm_device(V))
+    return {'workload': workload_desc(name, prob)['workload'], 'mvm_rhs_per_s': P / ms * 1e3, 'ms_per_step': ms,
+            'ms_per_step_sorted_order': ms_sorted,
+            'roofline_mvm': {'bound': 'hbm', 'alg_bytes_per_step': b_mvm, 'achieved': b_mvm / ms / 1e6, 'peak': peak,
+                             'unit': 'GB/s', 'frac': b_mvm / ms / 1e6 / peak,
+                             'frac_sorted_order': b_mvm / ms_sorted / 1e6 / peak},
+            'minres_iter_rhs_per_s': done / dt, 'minres_iterations_timed': K,
+            'minres_kernel_launches_per_iteration': launches / K,
+            'minres_host_launches_per_iteration': 'one cudaGraphLaunch + one 4-byte stop-flag copy',
+            'cpu_port_minres_iter_rhs_per_s': ncpu * K / dcpu, 'cpu_port_cores': 1,
+            'cpu_port_sample': '%d columns x %d iterations, serial' % (ncpu, K), 'parity': par}
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -229,13 +397,15 @@ def run_own(args):
     prob = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=CPL[args.workload])
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_rate(prob, steps=3, warmup=1)       # before CUDA is initialised (fork)
+        # before CUDA is initialised (fork); also times capped MINRES solves through the pool
+        cpu = cpu_reference_rate(prob, steps=3, warmup=1, solve_iters=8 if prob.n >= 100000 else 40, keep=True)
+    ref = _CPU_OP if _CPU_OP is not None else oracle_operator(prob)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from runlmc_b200 import _native as nat
     from runlmc_b200.fused import FusedLMC
-    from runlmc_b200.distributed import shard_bounds, sharded_gradient
+    from runlmc_b200.distributed import shard_bounds
     dev = torch.device('cuda', local)
     from runlmc_b200.kern import RBF
     op = FusedLMC(prob.Xs, prob.grids)                       # point sort on the device
@@ -257,24 +427,13 @@ def run_own(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    t_w = time.time()
-    while True:                                   # warm-up: >= W steps and long enough for the clocks to settle
-        for _ in range(args.warmup):
-            op.mvm_device(V, OUT)
-        torch.cuda.synchronize()
-        if time.time() - t_w > 0.5:
-            break
-    l0 = nat.lib.lmc_launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.window[0] = time.time()
-    e0.record()
-    for _ in range(args.steps):
+    for _ in range(max(args.warmup, 3)):
         op.mvm_device(V, OUT)
-    e1.record()
-    barrier()
+    torch.cuda.synchronize()
+    l0 = nat.lib.lmc_launch_count()
+    sampler.window[0] = time.time()
+    ms = timed_product(op, V, OUT, args.steps, args.warmup, barrier)
     sampler.window[1] = time.time()
-    ms = e0.elapsed_time(e1)
     launches = int(nat.lib.lmc_launch_count() - l0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -282,6 +441,16 @@ def run_own(args):
     ms = float(t.item())
     ms_step = ms / args.steps
     value = total_units * args.steps / (ms / 1e3)
+    # timed_product runs its warm-up passes inside the window: count only the timed launches
+    launches = launches * args.steps // max(1, (launches // max(1, launches // max(args.steps, 1))))
+    parity = parity_check(op, ref, Vh, OUT)
+    pe = torch.tensor([parity['max_rel_err_vs_oracle']], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pe, op=dist.ReduceOp.MAX)
+    parity['max_rel_err_vs_oracle'] = float(pe.item())
+    parity['ok'] = parity['max_rel_err_vs_oracle'] <= parity['tolerance']
+    parity['config'] = args.workload
+    parity['note'] = 'columns of every rank\'s shard of the timed block, max over ranks'
 
     # ---- end to end through host buffers: the public host API FusedLMC.mvm_into (C ABI
     # lmc_mvm_host) on pinned buffers; H2D copy of V and D2H copy of K~V are inside the timed
@@ -304,6 +473,7 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = total_units * e2e_steps / (float(t.item()) / 1e3)
     e2e_check = float(np.abs(Opn - OUT.cpu().numpy()).max())
+    e2e_parity = parity_check(op, ref, Vh, torch.as_tensor(Opn))
     clocks = sampler.summary()
     cnt = torch.tensor([float(P)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -311,10 +481,12 @@ def run_own(args):
     io_bytes = int(cnt.item()) * prob.n * 8
 
     # ---- per-family device time (separate pass so events do not perturb `value`) ----
+    l1 = nat.lib.lmc_launch_count()
     nat.profile_begin()
     for _ in range(args.steps):
         op.mvm_device(V, OUT)
     prof = nat.profile_end()
+    launches = int(nat.lib.lmc_launch_count() - l1)          # kernels of exactly `steps` products
     bins, gpitch = nat.lib.lmc_op_embed_bins(op._h), nat.lib.lmc_op_grid_cells(op._h)
     peak, peak_src = peaks()
     tot = sum(v[0] for v in prof.values()) or 1.0
@@ -336,58 +508,67 @@ def run_own(args):
                     'unit': 'GB/s', 'frac': b_mvm / ms_step / 1e6 / peak,
                     'note': 'whole product vs B_mvm = 16nP + 8dn + 8Q*bins + 8D (SURVEY.md sec.8d), this rank'}
 
-    # ---- the spectral stage against the fp64 roofline: pruned FFTs
-    # 2 * D * 2.5 * M~ log2 M~ * 3/4 plus the mix 4 D^2 bins flops per MVM and RHS ----
+    # ---- the spectral stage against the fp64 roofline: per MVM
+    # and RHS, pruned real FFTs 2 * D * 2.5 * M~ log2 M~ * 3/4 plus the mix 4 D^2 m~_c with m~_c the number
+    # of rfft bins (a complex RHS pair shares the full set of bins) ----
     fp64 = np.zeros(1)
     nat.check(nat.lib.lmc_fp64_peak(nat.host_ptr(fp64)))
     spectral_ms = sum(f['ms_per_step'] for f in fams if f['family'].startswith('fft') or f['family'] == 'mix')
-    flops_rhs = 2.0 * prob.D * 2.5 * bins * np.log2(bins) * 0.75 + 4.0 * prob.D ** 2 * bins
+    flops_rhs = 2.0 * prob.D * 2.5 * bins * np.log2(bins) * 0.75 + 4.0 * prob.D ** 2 * rfft_bins(op)
     roofline_fp64 = {'bound': 'fp64', 'stage': 'fft + mix + inverse fft', 'alg_flops_per_step': flops_rhs * P,
                      'achieved': flops_rhs * P / (spectral_ms * 1e-3) / 1e12 if spectral_ms else None,
                      'peak': float(fp64[0]), 'unit': 'TFLOP/s',
                      'frac': flops_rhs * P / (spectral_ms * 1e-3) / 1e12 / float(fp64[0]) if spectral_ms else None,
                      'peak_source': 'measured (lmc_fp64_peak: DFMA microbenchmark on this GPU)'}
 
-    # ---- one full stochastic gradient evaluation (solves + all partials) ----
-    grad = None
+    # ---- one full stochastic gradient evaluation (solves + all partials): the headline row uses
+    # hyper-parameters on which the reference's own stopping rule converges, the second
+    # row keeps the ill-conditioned operator the block product is timed on ----
+    grad = grad_ill = None
     if not args.no_grad:
-        barrier()
-        t0 = time.perf_counter()
-        grads, stats = sharded_gradient(op, prob.y, prob.probes, None, prob.coreg_vecs,
-                                        prob.coreg_mats(), tol=1e-4, rank=rank, world=world)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        nparams = sum(np.size(g) for g in grads[0]) + sum(np.size(g) for g in grads[1]) + \
-            sum(len(g) for g in grads[2]) + np.size(grads[3])
-        grad = {'grad_evals_per_s': 1.0 / dt, 'seconds': dt, 'mean_minres_iterations': stats['iterations'],
-                'mean_final_residual': stats['solv_error'], 'hyperparameters': int(nparams),
-                'minres_iter_rhs_per_s': stats['iterations'] * (prob.N + 1) / dt,
-                'includes': 'host->device copies of y/probes, N+1 MINRES solves (tol 1e-4, reference stopping rules), '
-                            'all partial derivatives, allreduce'}
-        # MINRES against B_minres_iter = 120 n bytes per iteration and RHS
-        it_rate = grad['minres_iter_rhs_per_s'] / world
-        grad['roofline_minres'] = {'bound': 'hbm', 'alg_bytes_per_iter_rhs': 120.0 * prob.n,
-                                   'achieved': 120.0 * prob.n * it_rate / 1e9, 'peak': peak, 'unit': 'GB/s',
-                                   'frac': 120.0 * prob.n * it_rate / 1e9 / peak, 'note': 'per GPU'}
-        if cpu is not None:
-            # the reference's path for the same evaluation: (N+1) solves x mean iterations products, on
-            # all host cores at the measured CPU product rate (solver vector work and partials not counted)
-            cpu_s = (prob.N + 1) * stats['iterations'] / cpu['value']
-            cpu['grad_eval_seconds_extrapolated'] = cpu_s
-            cpu['grad_evals_per_s_extrapolated'] = 1.0 / cpu_s
+        gp = GRAD_PARAMS.get(args.workload)
+        if gp:
+            pc = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=gp['cpl'], eps=gp['eps'])
+            op.set_kernels([RBF(g) for g in pc.gammas], pc.coreg_mats(), pc.noise, pc.coreg_vecs, pc.coreg_diags)
+            grad = gradient_row(op, pc, rank, world, dev, barrier, peak, 'converging',
+                                'lengthscales of %g..%g grid cells, noise ~ 1/Gamma(1 + 1/eps, 1) with eps = %g '
+                                '(the reference benchmark\'s noise parameter, benchlib/bench.py:111-115)'
+                                % (gp['cpl'], 4 * gp['cpl'], gp['eps']))
+            op.set_kernels([RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
+                           prob.coreg_diags)
+        if not args.no_ill:
+            grad_ill = gradient_row(op, prob, rank, world, dev, barrier, peak, 'ill_conditioned',
+                                    'the operator the block product is timed on (eps = 0.1): scipy\'s own stopping '
+                                    'rule ends above tol, the reference would log the solve as failed')
+        if grad is None:
+            grad, grad_ill = grad_ill, None
+        if cpu is not None and grad is not None:
+            # the reference's path for the same evaluation: N+1 solves x mean iterations on all host cores at
+            # the MEASURED rate of capped Pool solves (partials not counted)
+            rate = cpu.get('minres_iter_rhs_per_s')
+            if rate:
+                cpu_s = (prob.N + 1) * grad['mean_minres_iterations'] / rate
+                cpu['grad_eval_seconds_extrapolated'] = cpu_s
+                cpu['grad_evals_per_s_extrapolated'] = 1.0 / cpu_s
+                cpu['grad_extrapolation'] = '(N+1) x mean iterations of the headline gradient row / measured CPU ' \
+                                            'MINRES iteration rate'
+    extra = []
+    if rank == 0 and world == 1 and not args.no_configs:
+        for name in ('D', 'B', 'C', 'A'):
+            if name != args.workload:
+                extra.append(small_config_row(name, peak))
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_desc(args.workload, prob),
+                'timing': 'CUDA events on the launching stream, max over ranks',
                 'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': io_bytes, 'd2h_bytes_per_step': io_bytes,
                         'steps': e2e_steps, 'api': 'FusedLMC.mvm_into -> lmc_mvm_host (pinned host buffers, '
-                        'chunked copy/compute/copy pipeline)', 'max_abs_diff_vs_resident': e2e_check}, 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+                        'chunked copy/compute/copy pipeline)', 'max_abs_diff_vs_resident': e2e_check,
+                        'max_rel_err_vs_oracle': e2e_parity['max_rel_err_vs_oracle']},
+                'gpu_launches': launches, 'clocks': clocks, 'parity': parity, 'roofline': roofline,
                 'roofline_mvm': roofline_mvm, 'roofline_fp64': roofline_fp64, 'kernel_families': fams,
-                'gradient': grad}
+                'gradient': grad, 'gradient_ill_conditioned': grad_ill, 'configs': extra}
         if cpu is not None:
             line['cpu_baseline'] = cpu
         print(json.dumps(line))
@@ -405,7 +586,8 @@ def run_reference(args):
             'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': r['steps'], 'warmup': args.warmup,
             'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_desc(args.workload, prob), timing='host wall clock around Pool.map of the CPU products'),
+            'config': workload_desc(args.workload, prob),
+            'timing': 'host wall clock around Pool.map of the CPU products',
             'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -420,6 +602,8 @@ def main():
     ap.add_argument('--workload', default='E', choices=sorted(CPL))
     ap.add_argument('--no-grad', action='store_true', help='skip the gradient-evaluation leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--no-ill', action='store_true', help='skip the ill-conditioned gradient row')
+    ap.add_argument('--no-configs', action='store_true', help='skip the secondary workload rows')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
     # stdout carries exactly ONE line (the JSON): anything libraries print there while we run

@@ -138,6 +138,28 @@ int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* 
                     double tol, int maxiter, int check_every, int* iters_host,
                     double* resid_host, int* istop_host);
 
+/* ---- preconditioned MINRES ----------------------------------------------------
+ * The reference forwards an optional K.preconditioner to scipy as M (iterative.py:47-50: an SPD
+ * approximation of the INVERSE, y = M r); nothing in runlmc builds one.  The block solver runs scipy's
+ * preconditioned recurrence (minres.py:252-316: y = M r2, beta = sqrt(r2 . y), v = y / beta) per column;
+ * istop = 9 stands for scipy's ValueError on an indefinite M (the column keeps its last iterate).
+ * lmc_minres_pre: `precond` selects a preconditioner the library builds itself from the operator:
+ *   LMC_PRECOND_JACOBI  M = diag(K~)^-1, the exact diagonal (lmc_op_diagonal), refreshed after every
+ *                       parameter update.
+ * lmc_op_diagonal: diag(K~) in the caller's point order, host buffer [n].
+ * lmc_minres_generic_pre: lmc_minres_generic with a second callback that must leave M * scratch_in in
+ * scratch_out (any SPD operator composed by the caller).                                            */
+#define LMC_PRECOND_NONE 0
+#define LMC_PRECOND_JACOBI 1
+int lmc_minres_pre(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol,
+                   int maxiter, int check_every, int precond, int* iters_host, double* resid_host,
+                   int* istop_host, void* stream);
+int lmc_op_diagonal(lmc_op* op, double* diag_host);
+int lmc_minres_generic_pre(int (*apply_cb)(void*), int (*precond_cb)(void*), void* ctx, long n,
+                           double* scratch_in_dev, double* scratch_out_dev, const double* RHS_dev, long ld,
+                           int P, double* X_dev, double tol, int maxiter, int check_every, int* iters_host,
+                           double* resid_host, int* istop_host, void* stream);
+
 /* ---- batched conjugate gradients ---------------------------------------------
  * Iterative.solve(..., minres=False) (iterative.py:44-51): scipy.sparse.linalg.cg with M = I, x0 = 0,
  * rtol = min(1e-10, tol), atol = 0, maxiter, behind the same true-residual test every `check_every`-th

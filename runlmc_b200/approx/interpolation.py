@@ -100,19 +100,127 @@ def interp_bicubic(gridx, gridy, samples):
     return out
 
 
+class LazyCSR(scipy.sparse.csr_matrix):
+    """A scipy CSR matrix whose data / indices / indptr are built by `build()` the first time anything
+    reads them.  The fused device operator recomputes the interpolation weights from the coordinates
+    and never reads the CSR, so the reference's call sequence
+    ``W = multi_interpolant(Xs, *grids); WT = W.transpose().tocsr()`` (interpolated_llgp.py:431-437)
+    costs nothing on the host until a caller actually looks inside W (at n = 1M the eager build takes
+    seconds and 16 M nonzeros)."""
+
+    def __init__(self, arg1, shape=None, dtype=None, copy=False, build=None):
+        self.__dict__['_lazy'] = None
+        if build is None:       # scipy's own constructor calls (self.__class__(other) inside binary operators)
+            scipy.sparse.csr_matrix.__init__(self, arg1, shape=shape, dtype=dtype, copy=copy)
+            return
+        scipy.sparse.csr_matrix.__init__(self, (int(arg1[0]), int(arg1[1])), dtype=np.float64)
+        self.__dict__['_lazy'] = build      # the base constructor stored empty arrays: replaced on first read
+
+    def _materialize(self):
+        build = self.__dict__.get('_lazy')
+        if build is not None:
+            self.__dict__['_lazy'] = None
+            real = build()
+            self.__dict__['_d'], self.__dict__['_i'], self.__dict__['_p'] = real.data, real.indices, real.indptr
+
+    @property
+    def materialized(self):
+        return self.__dict__.get('_lazy') is None
+
+    def _get(self, key):
+        self._materialize()
+        return self.__dict__[key]
+
+    data = property(lambda self: self._get('_d'), lambda self, v: self.__dict__.__setitem__('_d', v))
+    indices = property(lambda self: self._get('_i'), lambda self, v: self.__dict__.__setitem__('_i', v))
+    indptr = property(lambda self: self._get('_p'), lambda self, v: self.__dict__.__setitem__('_p', v))
+
+    def transpose(self, axes=None, copy=False):
+        if self.materialized:
+            return scipy.sparse.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape).transpose(axes, copy)
+        return _LazyTranspose(self)
+
+    def __reduce__(self):
+        # pickles as the plain CSR it stands for (plus its attributes, e.g. lmc_geometry)
+        plain = scipy.sparse.csr_matrix((self.data, self.indices, self.indptr), shape=self.shape)
+        extra = {k: v for k, v in self.__dict__.items() if k in ('lmc_geometry',)}
+        return (_restore_csr, (plain, extra))
+
+
+def _restore_csr(plain, extra):
+    plain.__dict__.update(extra)
+    return plain
+
+
+class _LazyTranspose:
+    """`W.transpose()` of a LazyCSR that has not been built: only `.tocsr()` / `.shape` are offered,
+    which is what the reference's call sequence uses."""
+
+    def __init__(self, W):
+        self._W = W
+        self.shape = (W.shape[1], W.shape[0])
+
+    def tocsr(self, copy=False):
+        W = self._W
+
+        def build():
+            return scipy.sparse.csr_matrix((W.data, W.indices, W.indptr), shape=W.shape).transpose().tocsr()
+
+        return LazyCSR(self.shape, build=build)
+
+    def __getattr__(self, name):     # anything else: fall back to the real transposed matrix
+        W = self._W
+        real = scipy.sparse.csr_matrix((W.data, W.indices, W.indptr), shape=W.shape).transpose()
+        return getattr(real, name)
+
+
 def multi_interpolant(Xs, *inducing_grids):
     """Block-diagonal interpolant over outputs: row block d <-> column block
     [d*m, (d+1)*m) (interpolation.py:119-176).  The result carries
-    ``lmc_geometry = (Xs, grids)`` for the fused device operator."""
+    ``lmc_geometry = (Xs, grids)`` for the fused device operator, and is a LazyCSR: argument checks and
+    range warnings happen here, the CSR arrays are assembled only if something reads them."""
     grids = [np.asarray(g) for g in inducing_grids]
-    if Xs[0].ndim == 1 or Xs[0].shape[1] == 1:
-        Ws = [interp_cubic(grids[0], np.asarray(X).ravel()) for X in Xs]
-    else:
-        Ws = [interp_bicubic(grids[0], grids[1], np.asarray(X)) for X in Xs]
-    W = scipy.sparse.block_diag(Ws, format='csr') if len(Ws) > 1 else Ws[0].tocsr()
-    W = scipy.sparse.csr_matrix(W)
-    W.lmc_geometry = ([np.asarray(X) for X in Xs], grids)
+    Xs = [np.asarray(X) for X in Xs]
+    one_d = Xs[0].ndim == 1 or Xs[0].shape[1] == 1
+    m = int(np.prod([g.size for g in grids[:1 if one_d else 2]]))
+    n = int(sum(len(X) for X in Xs))
+    # the per-output argument checks and warnings of interp_cubic / interp_bicubic, without the assembly
+    for g in grids[:1 if one_d else 2]:
+        _check_grid('grid', g)
+    for X in Xs:
+        if len(X) == 0:
+            continue
+        if one_d:
+            _warn_range('', X.ravel(), grids[0])
+        else:
+            if X.ndim != 2 or X.shape[1] != 2:
+                raise ValueError('expecting 2d samples, got shape {}'.format(X.shape))
+            _warn_range('x ', X[:, 0], grids[0])
+            _warn_range('y ', X[:, 1], grids[1])
+
+    def build():
+        with _quiet():
+            if one_d:
+                Ws = [interp_cubic(grids[0], X.ravel()) for X in Xs]
+            else:
+                Ws = [interp_bicubic(grids[0], grids[1], X) for X in Xs]
+        W = scipy.sparse.block_diag(Ws, format='csr') if len(Ws) > 1 else Ws[0].tocsr()
+        return scipy.sparse.csr_matrix(W)
+
+    W = LazyCSR((n, len(Xs) * m), build=build)
+    W.lmc_geometry = (Xs, grids)
     return W
+
+
+class _quiet:
+    """The range warnings were already issued by multi_interpolant itself."""
+
+    def __enter__(self):
+        self._level = _LOG.level
+        _LOG.setLevel(logging.ERROR)
+
+    def __exit__(self, *exc):
+        _LOG.setLevel(self._level)
 
 
 def autogrid(Xs, lo, hi, m):

@@ -43,6 +43,20 @@ int op_set_params_dev(lmc_op* op, int Q, const double* top_dev, const double* B_
         rc = op->eng.spectrum(top_dev + (size_t)q * cells, op->spec + (size_t)q * bins, work, 0);
     op->fused = op->eng.fused_supported(D, Q) && getenv("LMC_NO_FUSED") == nullptr;
     if (e == cudaSuccess && rc == 0 && op->fused) rc = op->eng.spectrum_lines(op->spec, op->specL, op->specP, Q, 0);
+    // top values at the offsets (0..3, 0..3) a cubic stencil spans: all the Jacobi diagonal needs (precond.cu)
+    for (int q = 0; q < Q && e == cudaSuccess && rc == 0; ++q) {
+        double* t = op->t16 + 16 * q;
+        for (int i = 0; i < 16; ++i) t[i] = 0.0;
+        if (op->ndim == 2) {
+            e = cudaMemcpy2D(t, 4 * sizeof(double), top_dev + (size_t)q * cells, op->emb.m[1] * sizeof(double),
+                             4 * sizeof(double), 4, cudaMemcpyDeviceToHost);
+        } else {
+            double t4[4];
+            e = cudaMemcpy(t4, top_dev + (size_t)q * cells, sizeof(t4), cudaMemcpyDeviceToHost);
+            for (int i = 0; i < 4; ++i) t[4 * i] = t4[i];
+        }
+    }
+    op->jacobi_valid = false;
     if (e == cudaSuccess && rc == 0) e = cudaDeviceSynchronize();
     cudaFree(work);
     if (rc != 0) return rc;
@@ -173,6 +187,10 @@ int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_h
     LMC_REQUIRE(P >= 0 && ld >= op->ps.n, "bad block shape");
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
     const long n = op->ps.n;
+    // The pipeline runs on the handle's own non-blocking streams but shares its grid workspace with the
+    // stream-ordered entry points (lmc_mvm, lmc_minres, ...): wait for whatever they still have in
+    // flight, on any stream.  This entry point is synchronous anyway (it returns host data).
+    LMC_CHECK(cudaDeviceSynchronize());
     // chunk width: even, ~64 MB per buffer, at least 2 and at most 32 columns
     int chunk = (int)std::max<long>(2, std::min<long>(32, (64L << 20) / (8 * n)));
     chunk &= ~1;
@@ -286,6 +304,48 @@ int lmc_minres(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev,
     LMC_REQUIRE(op && RHS_dev && X_dev, "null argument");
     return minres_solve(op, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
                         istop_host, (cudaStream_t)stream);
+}
+
+// 1 / diag(K~) of the current parameters in sorted order, computed on first use after a parameter update
+static int ensure_jacobi(lmc_op* op, cudaStream_t st) {
+    if (op->jacobi_valid) return 0;
+    if (!op->jacobi) LMC_CHECK(cudaMalloc(&op->jacobi, sizeof(double) * (size_t)std::max<long>(op->ps.n, 1)));
+    LMC_TRY(op_jacobi(op, nullptr, op->jacobi, st));
+    LMC_CHECK(cudaStreamSynchronize(st));
+    op->jacobi_valid = true;
+    return 0;
+}
+
+int lmc_op_diagonal(lmc_op* op, double* diag_host) {
+    LMC_REQUIRE(op && diag_host, "null argument");
+    const long n = op->ps.n;
+    if (n == 0) return 0;
+    HostBlock sorted, caller;
+    LMC_CHECK(cudaMalloc(&sorted.p, sizeof(double) * n));
+    LMC_CHECK(cudaMalloc(&caller.p, sizeof(double) * n));
+    LMC_TRY(op_jacobi(op, sorted.p, nullptr, nullptr));
+    if (op->ps.identity) {
+        LMC_CHECK(cudaMemcpy(diag_host, sorted.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    } else {
+        LMC_TRY(permute_cols(op->ps, false, sorted.p, n, 1, caller.p, n, nullptr));
+        LMC_CHECK(cudaMemcpy(diag_host, caller.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int lmc_minres_pre(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol, int maxiter,
+                   int check_every, int precond, int* iters_host, double* resid_host, int* istop_host,
+                   void* stream) {
+    LMC_REQUIRE(op && RHS_dev && X_dev, "null argument");
+    LMC_REQUIRE(precond == LMC_PRECOND_NONE || precond == LMC_PRECOND_JACOBI, "unknown preconditioner");
+    const double* jac = nullptr;
+    if (precond == LMC_PRECOND_JACOBI) {
+        LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+        LMC_TRY(ensure_jacobi(op, (cudaStream_t)stream));
+        jac = op->jacobi;
+    }
+    return minres_solve(op, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+                        istop_host, (cudaStream_t)stream, jac);
 }
 
 int lmc_minres_host(lmc_op* op, const double* RHS_host, long ld, int P, double* X_host, double tol,

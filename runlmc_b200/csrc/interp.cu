@@ -12,6 +12,7 @@
 // accumulate onto the edge cell exactly like the reference's CSR `+=`
 // (interpolation.py:105-115).
 #include "interp.cuh"
+#include "interp_weights.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -167,26 +168,6 @@ void free_points(PointSet* ps) {
 // Keys weights of the 4 taps at cells i0-1, i0, i0+1, i0+2 for fractional offset u.
 // Written with explicit rounding steps (no FMA contraction) so the weights are
 // bit-identical to numpy's evaluation in the reference (interpolation.py:48-52).
-__device__ __forceinline__ double keys_near(double x) {  // |x| <= 1
-    double t = __dadd_rn(__dmul_rn(1.5, x), -2.5);
-    t = __dmul_rn(__dmul_rn(t, x), x);
-    return __dadd_rn(t, 1.0);
-}
-__device__ __forceinline__ double keys_far(double x) {  // 1 < |x| <= 2
-    double t = __dadd_rn(__dmul_rn(-0.5, x), 2.5);
-    t = __dadd_rn(__dmul_rn(t, x), -4.0);
-    return __dadd_rn(__dmul_rn(t, x), 2.0);
-}
-__device__ __forceinline__ void keys_weights(double u, double* w) {
-    const double x0 = __dadd_rn(u, 1.0);
-    w[0] = (x0 <= 1.0) ? keys_near(x0) : keys_far(x0);
-    w[1] = keys_near(u);
-    w[2] = keys_near(fabs(__dadd_rn(u, -1.0)));
-    w[3] = keys_far(fabs(__dadd_rn(u, -2.0)));
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-
 struct InterpArgs {
     const double* u0;
     const double* u1;

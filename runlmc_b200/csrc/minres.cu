@@ -16,6 +16,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace lmc {
@@ -79,17 +80,21 @@ __global__ void __launch_bounds__(kVecThreads) minres_init_kernel(
     if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
 }
 
-__global__ void minres_init_scalars_kernel(ColState* st, double* inv_beta, int* active, const double* part,
-                                           int nblk, int P, int* n_active) {
+// part_bb: partials of ||b||^2 (scipy returns x = 0 for b = 0); part: partials of beta1^2 = b . M b (the
+// same array without a preconditioner)
+__global__ void minres_init_scalars_kernel(ColState* st, double* inv_beta, int* active, const double* part_bb,
+                                           const double* part, int nblk, int P, int* n_active) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col < P) {
-        double s = 0.0;
-        for (int i = 0; i < nblk; ++i) s += part[(long)col * nblk + i];
+        double s = 0.0, bb = 0.0;
+        for (int i = 0; i < nblk; ++i) { s += part[(long)col * nblk + i]; bb += part_bb[(long)col * nblk + i]; }
         ColState c = {};
+        if (bb == 0.0) s = 0.0;
+        if (s < 0.0) { c.istop = 9; s = 0.0; }      // scipy: ValueError('indefinite preconditioner')
         c.beta1 = sqrt(s);
         c.beta = c.beta1; c.oldb = 0.0; c.dbar = 0.0; c.epsln = 0.0; c.phibar = c.beta1;
         c.rhs1 = c.beta1; c.rhs2 = 0.0; c.tnorm2 = 0.0; c.gmax = 0.0; c.gmin = DBL_MAX;
-        c.cs = -1.0; c.sn = 0.0; c.c_r1 = 0.0; c.istop = 0; c.itn = 0;
+        c.cs = -1.0; c.sn = 0.0; c.c_r1 = 0.0; c.itn = 0;
         c.done = (c.beta1 == 0.0) ? 1 : 0;  // scipy returns x = 0 at once
         st[col] = c;
         inv_beta[col] = c.done ? 0.0 : 1.0 / c.beta1;
@@ -99,10 +104,10 @@ __global__ void minres_init_scalars_kernel(ColState* st, double* inv_beta, int* 
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_active = -1;  // recomputed by the first status kernel
 }
 
-// y -= (beta/oldb) r1 ; alfa partial = sum (r2/beta) * y
+// y -= (beta/oldb) r1 ; alfa partial = sum (v/beta) * y   (v = r2, or M r2 with a preconditioner)
 __global__ void __launch_bounds__(kVecThreads) minres_k1_kernel(
-    double* y, const double* __restrict__ r1, const double* __restrict__ r2, const ColState* st,
-    const double* inv_beta, const int* active, long n, double* part, int nblk) {
+    double* y, const double* __restrict__ r1, const double* __restrict__ r2_unused, const double* __restrict__ vsrc,
+    const ColState* st, const double* inv_beta, const int* active, long n, double* part, int nblk) {
     const int col = blockIdx.y;
     if (!active[col]) return;
     const double c = st[col].c_r1, s = inv_beta[col];
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kVecThreads) minres_k1_kernel(
             double yv = y[o];
             if (c != 0.0) yv = __dsub_rn(yv, __dmul_rn(c, r1[o]));
             y[o] = yv;
-            acc = fma(__dmul_rn(s, r2[o]), yv, acc);
+            acc = fma(__dmul_rn(s, vsrc[o]), yv, acc);
         }
     }
     acc = block_reduce_sum(acc);
@@ -167,7 +172,9 @@ __global__ void minres_s1_kernel(ColState* st, const int* active, const double* 
     ColState c = st[col];
     c.itn += 1;
     c.oldb = c.beta;
-    c.beta = sqrt(s);
+    double s_pos = s;
+    if (s < 0.0) { c.istop = 9; s_pos = 0.0; }   // r2 . M r2 < 0: scipy raises (indefinite preconditioner)
+    c.beta = sqrt(s_pos);
     c.tnorm2 += c.alfa * c.alfa + c.oldb * c.oldb + c.beta * c.beta;
     if (c.itn == 1 && c.beta / c.beta1 <= 10 * DBL_EPSILON) c.istop = -1;
     c.oldeps = c.epsln;
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(kVecThreads) minres_k3_kernel(
     const int col = blockIdx.y;
     if (!active[col]) return;
     const ColState* c = st + col;
+    if (c->istop == 9) return;                   // x keeps the iterate before the failed step
     const double oldeps = c->oldeps, delta = c->delta, denom = c->denom, phi = c->phi, s = c->inv_oldb;
     const long base = (long)blockIdx.x * kVecChunk;
     double acc = 0.0;
@@ -322,6 +330,26 @@ static int reserve_workspace(void** p, size_t* cap, size_t bytes) {
     *cap = bytes;
     return 0;
 }
+
+SolverHost::~SolverHost() {
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (flags) cudaFreeHost(flags);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// pinned flags + events of the asynchronous stop test, and the solver's own stream (stream capture is
+// not allowed on the legacy default stream, which is what most callers pass)
+static int solver_host_init(SolverHost* h, bool own_stream) {
+    if (!h->flags) {
+        LMC_CHECK(cudaHostAlloc(&h->flags, sizeof(int) * SolverHost::kRing, cudaHostAllocDefault));
+        for (auto& e : h->ev) LMC_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        LMC_CHECK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    if (own_stream && !h->stream) LMC_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    return 0;
+}
+
 // The product the solver iterates with: out = A (in * in_scale) on [P][n] blocks
 struct MinresOperator {
     long n = 0;
@@ -330,6 +358,10 @@ struct MinresOperator {
                       cudaStream_t st) = 0;
     // device memory for the solver's state vectors, valid until the operator goes away
     virtual int workspace(size_t bytes, void** p) = 0;
+    virtual SolverHost* host() = 0;
+    // every product is a fixed sequence of launches of this library on the given stream, so an
+    // iteration can be captured into a CUDA graph and the solver may run on its own stream
+    virtual bool capturable() const { return false; }
     virtual ~MinresOperator() {}
 };
 
@@ -351,6 +383,8 @@ struct FusedOperator : MinresOperator {
         *p = op->solver_ws;
         return 0;
     }
+    SolverHost* host() override { return &op->solver_host; }
+    bool capturable() const override { return true; }
 };
 
 // Operator trees composed on the Python side: the solver fills `scratch_in`,
@@ -362,12 +396,14 @@ struct CallbackOperator : MinresOperator {
     double* scratch_out;
     void* ws = nullptr;
     size_t ws_cap = 0;
+    SolverHost sh;
     ~CallbackOperator() override { cudaFree(ws); }
     int workspace(size_t bytes, void** p) override {
         LMC_TRY(reserve_workspace(&ws, &ws_cap, bytes));
         *p = ws;
         return 0;
     }
+    SolverHost* host() override { return &sh; }
     int apply(const double* in, const double* in_scale, const int* active, double* out, int P,
               cudaStream_t st) override {
         (void)active;
@@ -383,6 +419,71 @@ struct CallbackOperator : MinresOperator {
     }
 };
 
+// The preconditioner M of scipy's minres (an SPD approximation of the inverse; y = M r, minres.py:256
+// and :313), forwarded by the reference from K.preconditioner (iterative.py:47-50).
+struct Preconditioner {
+    virtual int apply(const double* in, const int* active, double* out, long n, int P, cudaStream_t st) = 0;
+    virtual bool capturable() const { return false; }
+    virtual ~Preconditioner() {}
+};
+
+// out[c][i] = d[i] * in[c][i]  (Jacobi: d = 1 / diag K in the solver's point order)
+__global__ void __launch_bounds__(kVecThreads) diag_precond_kernel(const double* __restrict__ d,
+                                                                  const double* __restrict__ in,
+                                                                  const int* active, long n, double* out) {
+    const int col = blockIdx.y;
+    if (active && !active[col]) return;
+    const long base = (long)blockIdx.x * kVecChunk;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) out[(long)col * n + i] = __dmul_rn(d[i], in[(long)col * n + i]);
+    }
+}
+
+struct DiagPreconditioner : Preconditioner {
+    const double* d;   // [n] device, solver order
+    explicit DiagPreconditioner(const double* dd) : d(dd) {}
+    int apply(const double* in, const int* active, double* out, long n, int P, cudaStream_t st) override {
+        const dim3 grid((unsigned)ceil_div(n, kVecChunk), (unsigned)P);
+        diag_precond_kernel<<<grid, kVecThreads, 0, st>>>(d, in, active, n, out);
+        count_launch();
+        LMC_CHECK(cudaGetLastError());
+        return 0;
+    }
+    bool capturable() const override { return true; }
+};
+
+struct CallbackPreconditioner : Preconditioner {
+    int (*cb)(void*);
+    void* ctx;
+    double* scratch_in;
+    double* scratch_out;
+    int apply(const double* in, const int* active, double* out, long n, int P, cudaStream_t st) override {
+        (void)active;
+        LMC_CHECK(cudaMemcpyAsync(scratch_in, in, sizeof(double) * (size_t)P * n, cudaMemcpyDeviceToDevice, st));
+        const int rc = cb(ctx);
+        if (rc != 0) { set_error("preconditioner callback failed"); return 3; }
+        LMC_CHECK(cudaMemcpyAsync(out, scratch_out, sizeof(double) * (size_t)P * n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+};
+
+// partial sum_i a[c][i] * b[c][i]
+__global__ void __launch_bounds__(kVecThreads) minres_dot_kernel(const double* __restrict__ a,
+                                                                const double* __restrict__ b, const int* active,
+                                                                long n, double* part, int nblk) {
+    const int col = blockIdx.y;
+    if (active && !active[col]) return;
+    const long base = (long)blockIdx.x * kVecChunk;
+    double acc = 0.0;
+    for (int k = 0; k < kVecPerThread; ++k) {
+        const long i = base + k * kVecThreads + threadIdx.x;
+        if (i < n) acc = fma(a[(long)col * n + i], b[(long)col * n + i], acc);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) part[(long)col * nblk + blockIdx.x] = acc;
+}
+
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -395,96 +496,202 @@ struct WsSlice {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
-static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, double* X, double tol,
-                       int maxiter, int check_every, int* iters, double* resid, int* istop,
-                       cudaStream_t st) {
+// Everything one MINRES iteration touches; the vector buffers rotate by pointer, so the launches of
+// iteration k depend on k only through (k - 1) mod period (3 without, 6 with a preconditioner).
+struct MinresState {
+    long n; int P, nblk;
+    double *b, *x, *r1, *r2, *y, *wa, *wb, *wc;   // wa = older direction (scipy's w2), wb = newer (w), wc = free
+    double *z, *zold;                             // M r2 and the previous one (preconditioned only)
+    double *pa, *pb, *pc;
+    ColState* cs; double* inv_beta; int* active; int* n_active;
+    double rtol; int maxiter;
+};
+
+static int minres_iteration(MinresOperator& A, Preconditioner* M, MinresState& s, cudaStream_t st) {
+    const dim3 vgrid((unsigned)s.nblk, (unsigned)s.P);
+    const long n = s.n;
+    const double* v = M ? s.z : s.r2;             // v = (M r2) / beta, applied as a column scale
+    LMC_TRY(A.apply(v, s.inv_beta, s.active, s.y, s.P, st));
+    {
+        ProfScope prof(PROF_MINRES_VEC, st);
+        minres_k1_kernel<<<vgrid, kVecThreads, 0, st>>>(s.y, s.r1, s.r2, v, s.cs, s.inv_beta, s.active, n, s.pa, s.nblk);
+        minres_k2_kernel<<<vgrid, kVecThreads, 0, st>>>(s.y, s.r2, s.cs, s.active, n, s.pa, s.pb, s.nblk);
+    }
+    { double* t = s.r1; s.r1 = s.r2; s.r2 = s.y; s.y = t; }   // r1 <- r2 <- y ; old r1 buffer is the next y
+    count_launch(2);
+    if (M) {
+        { double* t = s.zold; s.zold = s.z; s.z = t; }
+        LMC_TRY(M->apply(s.r2, s.active, s.z, n, s.P, st));
+        ProfScope prof(PROF_MINRES_VEC, st);
+        minres_dot_kernel<<<vgrid, kVecThreads, 0, st>>>(s.r2, s.z, s.active, n, s.pb, s.nblk);
+        count_launch();
+    }
+    {
+        ProfScope prof(PROF_MINRES_SCALAR, st);
+        minres_s1_kernel<<<s.P, kScalarThreads, 0, st>>>(s.cs, s.active, s.pb, s.nblk, s.P, s.n_active);
+    }
+    {
+        // v = (previous M r2, or r1) / oldb
+        ProfScope prof(PROF_MINRES_VEC, st);
+        minres_k3_kernel<<<vgrid, kVecThreads, 0, st>>>(s.wc, s.wa, s.wb, M ? s.zold : s.r1, s.x, s.cs, s.active, n,
+                                                        s.pc, s.nblk);
+    }
+    { double* t = s.wa; s.wa = s.wb; s.wb = s.wc; s.wc = t; }
+    {
+        ProfScope prof(PROF_MINRES_SCALAR, st);
+        minres_s2_kernel<<<s.P, kScalarThreads, 0, st>>>(s.cs, s.inv_beta, s.active, s.pc, s.nblk, s.P, s.rtol,
+                                                         s.maxiter, s.n_active);
+    }
+    count_launch(3);
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+struct GraphSet {
+    cudaGraphExec_t exec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~GraphSet() { for (auto& e : exec) if (e) cudaGraphExecDestroy(e); }
+};
+
+static bool graphs_enabled() {
+    static const bool off = getenv("LMC_NO_GRAPH") != nullptr;
+    return !off;
+}
+
+static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, long ld, int P, double* X,
+                       double tol, int maxiter, int check_every, int* iters, double* resid, int* istop,
+                       cudaStream_t caller_st) {
     LMC_REQUIRE(P >= 1, "need at least one right-hand side");
     LMC_REQUIRE(maxiter >= 1 && check_every >= 1, "maxiter/check_every must be positive");
     const long n = A.n;
     LMC_REQUIRE(ld >= n, "leading dimension < n");
     const int nblk = ceil_div(n, kVecChunk);
-    const double rtol = std::fmin(1e-10, tol);
     const size_t vec = sizeof(double) * (size_t)P * n;
-    DevBuf parts[3], stb, invb, act, nact;
     const size_t vec_al = (vec + 255) & ~(size_t)255;
+    const int nvec = M ? 10 : 8;
+    // one grow-only allocation: state vectors, then the per-CTA partials and the per-column scalars
+    const size_t part_al = (sizeof(double) * (size_t)P * nblk + 255) & ~(size_t)255;
+    const size_t cs_al = (sizeof(ColState) * (size_t)P + 255) & ~(size_t)255;
+    const size_t col_al = (sizeof(double) * (size_t)P + 255) & ~(size_t)255;
     void* ws = nullptr;
-    LMC_TRY(A.workspace(vec_al * 8, &ws));
-    WsSlice bufs[8];
-    for (int i = 0; i < 8; ++i) bufs[i].p = static_cast<char*>(ws) + vec_al * i;
-    for (auto& b : parts) LMC_TRY(b.alloc(sizeof(double) * (size_t)P * nblk));
-    LMC_TRY(stb.alloc(sizeof(ColState) * P));
-    LMC_TRY(invb.alloc(sizeof(double) * P));
-    LMC_TRY(act.alloc(sizeof(int) * P));
-    LMC_TRY(nact.alloc(sizeof(int)));
-    double *b = bufs[0].as<double>(), *x = bufs[1].as<double>();
-    double *r1 = bufs[2].as<double>(), *r2 = bufs[3].as<double>(), *y = bufs[4].as<double>();
-    // wa = older direction (scipy's w2), wb = newer (scipy's w), wc = free buffer
-    double *wa = bufs[5].as<double>(), *wb = bufs[6].as<double>(), *wc = bufs[7].as<double>();
-    double *pa = parts[0].as<double>(), *pb = parts[1].as<double>(), *pc = parts[2].as<double>();
-    ColState* cs = stb.as<ColState>();
-    double* inv_beta = invb.as<double>();
-    int* active = act.as<int>();
-    int* n_active = nact.as<int>();
+    LMC_TRY(A.workspace(vec_al * nvec + 3 * part_al + cs_al + 2 * col_al + 256, &ws));
+    char* base = static_cast<char*>(ws);
+    WsSlice bufs[10];
+    for (int i = 0; i < nvec; ++i) bufs[i].p = base + vec_al * i;
+    char* tail = base + vec_al * nvec;
+    MinresState s = {};
+    s.n = n; s.P = P; s.nblk = nblk;
+    s.b = bufs[0].as<double>(); s.x = bufs[1].as<double>();
+    s.r1 = bufs[2].as<double>(); s.r2 = bufs[3].as<double>(); s.y = bufs[4].as<double>();
+    s.wa = bufs[5].as<double>(); s.wb = bufs[6].as<double>(); s.wc = bufs[7].as<double>();
+    s.z = M ? bufs[8].as<double>() : nullptr; s.zold = M ? bufs[9].as<double>() : nullptr;
+    s.pa = reinterpret_cast<double*>(tail); s.pb = reinterpret_cast<double*>(tail + part_al);
+    s.pc = reinterpret_cast<double*>(tail + 2 * part_al);
+    s.cs = reinterpret_cast<ColState*>(tail + 3 * part_al);
+    s.inv_beta = reinterpret_cast<double*>(tail + 3 * part_al + cs_al);
+    s.active = reinterpret_cast<int*>(tail + 3 * part_al + cs_al + col_al);
+    s.n_active = reinterpret_cast<int*>(tail + 3 * part_al + cs_al + 2 * col_al);
+    s.rtol = std::fmin(1e-10, tol); s.maxiter = maxiter;
     const int* perm = A.perm;
     const dim3 vgrid((unsigned)nblk, (unsigned)P);
     const int sthreads = 128, sblocks = ceil_div(P, sthreads);
 
-    minres_init_kernel<<<vgrid, kVecThreads, 0, st>>>(RHS, ld, perm, n, b, r2, x, wa, wb, wc, pa, nblk);
-    minres_init_scalars_kernel<<<sblocks, sthreads, 0, st>>>(cs, inv_beta, active, pa, nblk, P, n_active);
-    count_launch(2);
+    // Graph capture needs a capturing-capable stream and products made of this library's launches only;
+    // the per-family event timing (lmc_profile_*) wants the plain launches.
+    const bool use_graph = graphs_enabled() && A.capturable() && (!M || M->capturable()) && !g_prof_on;
+    SolverHost* sh = A.host();
+    LMC_TRY(solver_host_init(sh, use_graph));
+    cudaStream_t st = caller_st;
+    if (use_graph) {
+        st = sh->stream;
+        LMC_CHECK(cudaEventRecord(sh->ev_join, caller_st));
+        LMC_CHECK(cudaStreamWaitEvent(st, sh->ev_join, 0));
+    }
+
+    minres_init_kernel<<<vgrid, kVecThreads, 0, st>>>(RHS, ld, perm, n, s.b, s.r2, s.x, s.wa, s.wb, s.wc, s.pa, nblk);
+    count_launch();
+    if (M) {
+        LMC_TRY(M->apply(s.r2, nullptr, s.z, n, P, st));                 // y = M r1, beta1^2 = r1 . y
+        minres_dot_kernel<<<vgrid, kVecThreads, 0, st>>>(s.r2, s.z, nullptr, n, s.pb, nblk);
+        count_launch();
+    }
+    minres_init_scalars_kernel<<<sblocks, sthreads, 0, st>>>(s.cs, s.inv_beta, s.active, s.pa, M ? s.pb : s.pa, nblk, P,
+                                                           s.n_active);
+    count_launch();
     LMC_CHECK(cudaGetLastError());
 
-    int h_active = P;
-    const int poll = 8;
-    for (int itn = 1; itn <= maxiter; ++itn) {
-        // y = K (r2 / beta)
-        LMC_TRY(A.apply(r2, inv_beta, active, y, P, st));
-        {
-            ProfScope prof(PROF_MINRES_VEC, st);
-            minres_k1_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r1, r2, cs, inv_beta, active, n, pa, nblk);
-            minres_k2_kernel<<<vgrid, kVecThreads, 0, st>>>(y, r2, cs, active, n, pa, pb, nblk);
+    const int period = M ? 6 : 3;
+    GraphSet graphs;
+    int head = 0, tail_i = 0;          // ring of outstanding stop-flag reads: [tail_i, head)
+    bool stop = false;
+    auto drain = [&](bool block) -> int {
+        while (tail_i < head) {
+            const int slot = tail_i % SolverHost::kRing;
+            if (block || head - tail_i >= SolverHost::kRing) {
+                LMC_CHECK(cudaEventSynchronize(sh->ev[slot]));
+            } else {
+                const cudaError_t q = cudaEventQuery(sh->ev[slot]);
+                if (q == cudaErrorNotReady) break;
+                LMC_CHECK(q);
+            }
+            if (sh->flags[slot] == 0) stop = true;
+            ++tail_i;
         }
-        { double* t = r1; r1 = r2; r2 = y; y = t; }   // r1 <- r2 <- y ; old r1 buffer is the next y
-        {
-            ProfScope prof(PROF_MINRES_SCALAR, st);
-            minres_s1_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pb, nblk, P, n_active);
+        return 0;
+    };
+    for (int itn = 1; itn <= maxiter && !stop; ++itn) {
+        const int phase = (itn - 1) % period;
+        if (use_graph && itn >= 2) {
+            if (!graphs.exec[phase]) {
+                // capture this iteration (the buffer rotation inside minres_iteration is host state and
+                // advances exactly as in the eager path)
+                cudaGraph_t g = nullptr;
+                LMC_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const int rc = minres_iteration(A, M, s, st);
+                const cudaError_t e = cudaStreamEndCapture(st, &g);
+                if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
+                LMC_CHECK(e);
+                const cudaError_t ei = cudaGraphInstantiate(&graphs.exec[phase], g, 0);
+                cudaGraphDestroy(g);
+                LMC_CHECK(ei);
+            } else {
+                // same launches as the captured ones: only advance the host-side rotation
+                { double* t = s.r1; s.r1 = s.r2; s.r2 = s.y; s.y = t; }
+                if (M) { double* t = s.zold; s.zold = s.z; s.z = t; }
+                { double* t = s.wa; s.wa = s.wb; s.wb = s.wc; s.wc = t; }
+                count_launch(M ? 7 : 5);
+            }
+            LMC_CHECK(cudaGraphLaunch(graphs.exec[phase], st));
+        } else {
+            LMC_TRY(minres_iteration(A, M, s, st));
         }
-        {
-            // v = r1 / oldb
-            ProfScope prof(PROF_MINRES_VEC, st);
-            minres_k3_kernel<<<vgrid, kVecThreads, 0, st>>>(wc, wa, wb, r1, x, cs, active, n, pc, nblk);
-        }
-        { double* t = wa; wa = wb; wb = wc; wc = t; }
-        {
-            ProfScope prof(PROF_MINRES_SCALAR, st);
-            minres_s2_kernel<<<P, kScalarThreads, 0, st>>>(cs, inv_beta, active, pc, nblk, P, rtol, maxiter, n_active);
-        }
-        count_launch(5);
-        bool polled = false;
         if (itn % check_every == 0) {
             // reference callback: true residual of the columns still running
-            LMC_TRY(A.apply(x, nullptr, active, y, P, st));
-            minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, active, n, pa, nblk);
-            LMC_CHECK(cudaMemsetAsync(n_active, 0, sizeof(int), st));
-            minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 0, n_active);
+            LMC_TRY(A.apply(s.x, nullptr, s.active, s.y, P, st));
+            minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(s.b, s.y, s.active, n, s.pa, nblk);
+            LMC_CHECK(cudaMemsetAsync(s.n_active, 0, sizeof(int), st));
+            minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(s.cs, s.active, s.pa, nblk, P, tol, 0, s.n_active);
             count_launch(2);
-            polled = true;
         }
-        if (polled || itn % poll == 0 || itn == maxiter) {
-            LMC_CHECK(cudaMemcpyAsync(&h_active, n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-            LMC_CHECK(cudaStreamSynchronize(st));
-            if (h_active == 0) break;
+        // asynchronous stop test: the count of running columns lands in pinned memory; the host reads
+        // it when the copy's event has fired, at most kRing iterations later.  Iterations enqueued
+        // after every column has stopped find no active column and do nothing.
+        {
+            const int slot = head % SolverHost::kRing;
+            LMC_CHECK(cudaMemcpyAsync(&sh->flags[slot], s.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LMC_CHECK(cudaEventRecord(sh->ev[slot], st));
+            ++head;
         }
+        LMC_TRY(drain(itn == maxiter));
     }
     // final residual of every column (iterative.py:53)
-    LMC_TRY(A.apply(x, nullptr, nullptr, y, P, st));
-    minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(b, y, nullptr, n, pa, nblk);
-    minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(cs, active, pa, nblk, P, tol, 1, n_active);
-    minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(x, perm, n, X, ld);
+    LMC_TRY(A.apply(s.x, nullptr, nullptr, s.y, P, st));
+    minres_resid_kernel<<<vgrid, kVecThreads, 0, st>>>(s.b, s.y, nullptr, n, s.pa, nblk);
+    minres_s3_kernel<<<P, kScalarThreads, 0, st>>>(s.cs, s.active, s.pa, nblk, P, tol, 1, s.n_active);
+    minres_finish_kernel<<<vgrid, kVecThreads, 0, st>>>(s.x, perm, n, X, ld);
     count_launch(3);
     LMC_CHECK(cudaGetLastError());
     std::vector<ColState> h((size_t)P);
-    LMC_CHECK(cudaMemcpyAsync(h.data(), cs, sizeof(ColState) * P, cudaMemcpyDeviceToHost, st));
+    LMC_CHECK(cudaMemcpyAsync(h.data(), s.cs, sizeof(ColState) * P, cudaMemcpyDeviceToHost, st));
     LMC_CHECK(cudaStreamSynchronize(st));
     for (int c = 0; c < P; ++c) {
         if (iters) iters[c] = h[c].itn;
@@ -495,10 +702,14 @@ static int minres_core(MinresOperator& A, const double* RHS, long ld, int P, dou
 }
 
 int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
-                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st) {
+                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st, const double* jacobi) {
     LMC_REQUIRE(op->Q > 0, "operator parameters not set");
     FusedOperator A(op);
-    return minres_core(A, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st);
+    if (jacobi) {
+        DiagPreconditioner M(jacobi);
+        return minres_core(A, &M, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st);
+    }
+    return minres_core(A, nullptr, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st);
 }
 
 
@@ -768,7 +979,22 @@ int lmc_minres_generic(int (*apply_cb)(void*), void* ctx, long n, double* scratc
     CallbackOperator A;
     A.n = n; A.perm = nullptr; A.cb = apply_cb; A.ctx = ctx;
     A.scratch_in = scratch_in_dev; A.scratch_out = scratch_out_dev;
-    return minres_core(A, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+    return minres_core(A, nullptr, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+                       istop_host, (cudaStream_t)stream);
+}
+
+int lmc_minres_generic_pre(int (*apply_cb)(void*), int (*precond_cb)(void*), void* ctx, long n,
+                           double* scratch_in_dev, double* scratch_out_dev, const double* RHS_dev, long ld,
+                           int P, double* X_dev, double tol, int maxiter, int check_every, int* iters_host,
+                           double* resid_host, int* istop_host, void* stream) {
+    LMC_REQUIRE(apply_cb && precond_cb && scratch_in_dev && scratch_out_dev && RHS_dev && X_dev, "null argument");
+    LMC_REQUIRE(n >= 1 && ld >= n, "bad block shape");
+    CallbackOperator A;
+    A.n = n; A.perm = nullptr; A.cb = apply_cb; A.ctx = ctx;
+    A.scratch_in = scratch_in_dev; A.scratch_out = scratch_out_dev;
+    CallbackPreconditioner M;
+    M.cb = precond_cb; M.ctx = ctx; M.scratch_in = scratch_in_dev; M.scratch_out = scratch_out_dev;
+    return minres_core(A, &M, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
                        istop_host, (cudaStream_t)stream);
 }
 

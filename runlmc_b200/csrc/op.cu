@@ -154,6 +154,7 @@ lmc_op::~lmc_op() {
     cudaFree(S);
     cudaFree(Vs);
     cudaFree(solver_ws);
+    cudaFree(jacobi);
 }
 
 lmc_bttb::~lmc_bttb() {

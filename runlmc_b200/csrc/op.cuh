@@ -5,6 +5,19 @@
 #include "spectral.cuh"
 #include <vector>
 
+namespace lmc {
+// Host-side state of the block solvers that outlives a solve: pinned flags and events of the
+// asynchronous stop test, and the stream iterations are captured on.
+struct SolverHost {
+    static const int kRing = 4;
+    int* flags = nullptr;                  // pinned, [kRing]
+    cudaEvent_t ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join = nullptr;
+    cudaStream_t stream = nullptr;
+    ~SolverHost();
+};
+}  // namespace lmc
+
 struct lmc_op {
     int D = 0, ndim = 0, Q = 0;
     lmc::Embedding emb;
@@ -46,6 +59,10 @@ struct lmc_op {
     // cudaMalloc/cudaFree of ~8 n P doubles per solve would cost as much as tens of iterations
     void* solver_ws = nullptr;
     size_t solver_ws_cap = 0;
+    lmc::SolverHost solver_host;
+    double* jacobi = nullptr;      // [n] 1 / diag(K~) in sorted order, valid for the current parameters if jacobi_valid
+    bool jacobi_valid = false;
+    double t16[64 * 16] = {0};     // top_q at the offsets (0..3, 0..3) a cubic stencil spans, per kernel (Q <= 64)
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     ~lmc_op();
@@ -73,11 +90,16 @@ int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st);
 int op_grid_apply(lmc_op* op, cplx* G, int npairs, int Q, const double* spec, const double* B,
                   cudaStream_t st);
 
+// jacobi: optional [n] device vector 1 / diag(K~) in sorted order = scipy's M (iterative.py:47)
 int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
-                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st);
+                 int check_every, int* iters, double* resid, int* istop, cudaStream_t st,
+                 const double* jacobi = nullptr);
 
 int cg_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
              int check_every, int* iters, double* resid, int* info, cudaStream_t st);
+
+// diag(K~) and / or its reciprocal in sorted order (either pointer may be null); precond.cu
+int op_jacobi(lmc_op* op, double* diag_sorted, double* inv_sorted, cudaStream_t st);
 
 // tops_extra: [ntops_extra][cells] derivative tops, host memory unless extra_on_device
 int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* RINV, long ld, int N,

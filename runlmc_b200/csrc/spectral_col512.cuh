@@ -123,8 +123,8 @@ struct Col512Args {
     const cplx* tw1;          // [15][32]  W512^{m c}
 };
 
-template <int D, class MIX>
-__global__ void __launch_bounds__(32 * D, (D <= 10 ? 2 : 1)) fused_col512_kernel(const Col512Args a, const MIX mb) {
+template <int D, class MIX, int MINB>
+__global__ void __launch_bounds__(32 * D, MINB) fused_col512_kernel(const Col512Args a, const MIX mb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* tw = reinterpret_cast<cplx*>(smem_raw);
     cplx* bufs = tw + kC512Tw;                    // [D][kC512Line]
@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(32 * D, (D <= 10 ? 2 : 1)) fused_col512_kernel
         const long pair = (long)blockIdx.y * a.ppc + pp;
         if (pair >= a.npairs) break;              // uniform over the CTA
         cplx* g = a.data + (pair * D + warp) * a.slab_stride + (long)line * a.line_stride + lane;
+        if (pp + 1 < a.ppc && pair + 1 < a.npairs && 8 * lane < a.valid) {
+            // the next pair's line of this warp: start it on its way from HBM to L2 now (128 B per lane)
+            const cplx* nx = g - lane + (long)D * a.slab_stride + 8 * lane;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        }
         cplx x[16];
         // ---- forward ----
 #pragma unroll
@@ -179,9 +184,7 @@ __global__ void __launch_bounds__(32 * D, (D <= 10 ? 2 : 1)) fused_col512_kernel
             const long qstride = (long)a.n_lines * 512;
 #pragma unroll
             for (int q = 0; q < MIX::NQ; ++q) f[q] = (MIX::NQ <= 4 || q < a.Q) ? __ldg(sp + q * qstride) : 0.0;
-            mb.apply(f, a.Q, v);
-#pragma unroll
-            for (int d = 0; d < D; ++d) bufs[d * kC512Line + p] = v[d];
+            mb.apply_store(f, a.Q, v, bufs + p, kC512Line);
         }
         __syncthreads();
         // ---- inverse ----

@@ -51,17 +51,36 @@ struct MixB {
 #pragma unroll
         for (int d = 0; d < D; ++d) x[d] = y[d];
     }
+    // Same product with every output written to dst[dp * stride] as soon as it is complete (x is in
+    // registers, so dst may be where x came from): no second register array.
+    __device__ __forceinline__ void apply_store(const double* f, int Q, const cplx* x, cplx* dst, int stride) const {
+#pragma unroll
+        for (int dp = 0; dp < D; ++dp) {
+            double yr = 0.0, yi = 0.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double m = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (q < Q) m = fma(f[q], b[q][dp][d], m);   // warp-uniform
+                yr = fma(m, x[d].x, yr);
+                yi = fma(m, x[d].y, yi);
+            }
+            dst[dp * stride] = make_double2(yr, yi);
+        }
+    }
 };
 
 static const int kMaxRankPerKernel = 2;   // low-rank path: every B_q has rank <= 2 (+ diagonal)
 // NQ = number of kernels the struct holds: Q itself for Q <= 4 (loops fully unrolled, no per-q
-// branches, Q spectrum loads per bin), or 8 with run-time Q.
-template <int D, int NQ_>
+// branches, Q spectrum loads per bin), or 8 with run-time Q.  RK = largest rank among the kernels
+// (compile time; lower-rank kernels are zero padded), so no rank test is left in the inner loops.
+template <int D, int NQ_, int RK_>
 struct MixLR {
     static const int NQ = NQ_;
-    double a[NQ][kMaxRankPerKernel][D];
+    static const int RK = RK_;
+    double a[NQ][RK][D];
     double kappa[NQ][D];
-    int rank[NQ];
     // In place.  The mix is a real matrix, so the real and the imaginary parts of the bin are two
     // independent real products: they are done one after the other with one set of D accumulators,
     // which keeps the live registers at ~3D doubles (x complex + y) instead of 5D.
@@ -75,15 +94,13 @@ struct MixLR {
             for (int q = 0; q < NQ; ++q) {
                 if (NQ <= 4 || q < Q) {   // warp-uniform
 #pragma unroll
-                    for (int r = 0; r < kMaxRankPerKernel; ++r) {
-                        if (r < rank[q]) {   // warp-uniform
-                            double t = 0.0;
+                    for (int r = 0; r < RK; ++r) {
+                        double t = 0.0;
 #pragma unroll
-                            for (int d = 0; d < D; ++d) t = fma(a[q][r][d], part ? x[d].y : x[d].x, t);
-                            t *= f[q];
+                        for (int d = 0; d < D; ++d) t = fma(a[q][r][d], part ? x[d].y : x[d].x, t);
+                        t *= f[q];
 #pragma unroll
-                            for (int d = 0; d < D; ++d) y[d] = fma(a[q][r][d], t, y[d]);
-                        }
+                        for (int d = 0; d < D; ++d) y[d] = fma(a[q][r][d], t, y[d]);
                     }
                 }
             }
@@ -98,6 +115,49 @@ struct MixLR {
                 if (part) x[d].y = fma(ks, x[d].y, y[d]);
                 else x[d].x = fma(ks, x[d].x, y[d]);
             }
+        }
+    }
+    // Both parts at once without an accumulator array: first the projections t_{q,r} = f_q (a_{q,r} . x)
+    // (complex, 2 Q RK doubles), then every output y_d = (sum_q f_q kappa_q[d]) x_d + sum a_{q,r}[d] t_{q,r}
+    // is written to dst[d * stride] as soon as it is complete (x is in registers, so dst may be where x came
+    // from).  Live values: x (2 D doubles) + t; Q RK (4 D + 2) + (Q + 2) D fp64 operations per bin.
+    __device__ __forceinline__ void apply_store(const double* f, int Q, const cplx* x, cplx* dst, int stride) const {
+        cplx t[NQ][RK];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+            for (int r = 0; r < RK; ++r) {
+                double tr = 0.0, ti = 0.0;
+                if (NQ <= 4 || q < Q) {   // warp-uniform
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        tr = fma(a[q][r][d], x[d].x, tr);
+                        ti = fma(a[q][r][d], x[d].y, ti);
+                    }
+                    tr *= f[q];
+                    ti *= f[q];
+                }
+                t[q][r] = make_double2(tr, ti);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double ks = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (NQ <= 4 || q < Q) ks = fma(f[q], kappa[q][d], ks);
+            double yr = ks * x[d].x, yi = ks * x[d].y;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (NQ <= 4 || q < Q) {
+#pragma unroll
+                    for (int r = 0; r < RK; ++r) {
+                        yr = fma(a[q][r][d], t[q][r].x, yr);
+                        yi = fma(a[q][r][d], t[q][r].y, yi);
+                    }
+                }
+            }
+            dst[d * stride] = make_double2(yr, yi);
         }
     }
 };
@@ -174,20 +234,23 @@ static inline bool use_col512(const FusedArgs& a) {
 
 template <int D, class MIX>
 static int launch_col512_kernel(const FusedArgs& a, const MIX& m, int npairs, cudaStream_t st) {
-    static const int ppc_env = getenv("LMC_COL512_PPC") ? atoi(getenv("LMC_COL512_PPC")) : 1;
+    static const int ppc_env = getenv("LMC_COL512_PPC") ? atoi(getenv("LMC_COL512_PPC")) : 4;
     const size_t smem = sizeof(cplx) * (size_t)(kC512Tw + D * kC512Line);
+    constexpr int MINB = D <= 10 ? 2 : 1;
     static bool attr = false;
     if (!attr) {
-        LMC_CHECK(cudaFuncSetAttribute(fused_col512_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LMC_CHECK(cudaFuncSetAttribute(fused_col512_kernel<D, MIX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kFusedSmemMax));
         attr = true;
     }
     Col512Args c = {};
     c.data = a.data; c.slab_stride = a.slab_stride; c.line_stride = a.line_stride;
-    c.n_lines = a.n_lines; c.valid = a.valid; c.npairs = npairs; c.ppc = std::max(1, ppc_env);
+    // pairs per CTA: amortises the twiddle table and lets a CTA prefetch its next lines; keep >= 4 waves of CTAs
+    c.n_lines = a.n_lines; c.valid = a.valid; c.npairs = npairs;
+    c.ppc = std::max(1, std::min(ppc_env, (int)((long)a.n_lines * npairs / (4 * 296))));
     c.Q = a.Q; c.specP = a.specP; c.tw1 = a.tw512;
     dim3 grid((unsigned)a.n_lines, (unsigned)ceil_div(npairs, c.ppc));
-    fused_col512_kernel<D, MIX><<<grid, 32 * D, smem, st>>>(c, m);
+    fused_col512_kernel<D, MIX, MINB><<<grid, 32 * D, smem, st>>>(c, m);
     return 0;
 }
 
@@ -205,18 +268,29 @@ static int launch_fused_kernel(const FusedArgs& a, const MIX& m, dim3 grid, int 
     return 0;
 }
 
-template <int D, int NQ>
+template <int D, int NQ, int RK>
 static int launch_fused_lowrank(const FusedArgs& a, const MixSpec& mix, dim3 grid, int threads, size_t smem,
                                 cudaStream_t st) {
-    MixLR<D, NQ> ml = {};     // kernel parameter, copied at launch
+    MixLR<D, NQ, RK> ml = {};     // kernel parameter, copied at launch; kernels of lower rank stay zero padded
     int r = 0;
     for (int q = 0; q < a.Q; ++q) {
-        ml.rank[q] = mix.ranks[q];
         for (int k = 0; k < mix.ranks[q]; ++k, ++r)
             for (int d = 0; d < D; ++d) ml.a[q][k][d] = mix.A[(size_t)r * D + d];
         for (int d = 0; d < D; ++d) ml.kappa[q][d] = mix.kappa[(size_t)q * D + d];
     }
     return launch_fused_kernel<D>(a, ml, grid, threads, smem, st);
+}
+
+template <int D, int RK>
+static int launch_fused_lowrank_q(const FusedArgs& a, const MixSpec& mix, dim3 grid, int threads, size_t smem,
+                                  cudaStream_t st) {
+    switch (a.Q) {
+        case 1: return launch_fused_lowrank<D, 1, RK>(a, mix, grid, threads, smem, st);
+        case 2: return launch_fused_lowrank<D, 2, RK>(a, mix, grid, threads, smem, st);
+        case 3: return launch_fused_lowrank<D, 3, RK>(a, mix, grid, threads, smem, st);
+        case 4: return launch_fused_lowrank<D, 4, RK>(a, mix, grid, threads, smem, st);
+        default: return launch_fused_lowrank<D, 8, RK>(a, mix, grid, threads, smem, st);
+    }
 }
 
 template <int D>
@@ -228,8 +302,9 @@ int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, in
             total_rank += mix.ranks[q];
             max_rank = std::max(max_rank, mix.ranks[q]);
         }
+    // cost of the zero-padded low-rank form against the dense one
     const bool lowrank = mix.ranks && max_rank <= kMaxRankPerKernel &&
-                         total_rank * (4 * D + 2) + (a.Q + 2) * D < (a.Q + 2) * D * D;
+                         a.Q * std::max(max_rank, 1) * (4 * D + 2) + (a.Q + 2) * D < (a.Q + 2) * D * D;
     a.plan = make_plan(a.L);
     a.lay = stage_tw_layout(a.L, a.plan);
     a.tw_total = a.lay.total;
@@ -246,14 +321,10 @@ int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, in
     dim3 grid((unsigned)ceil_div(a.n_lines, lpc), (unsigned)npairs);
     ProfScope prof(PROF_MIX, st);
     int rc;
+    (void)total_rank;
     if (lowrank) {
-        switch (a.Q) {
-            case 1: rc = launch_fused_lowrank<D, 1>(a, mix, grid, threads, smem, st); break;
-            case 2: rc = launch_fused_lowrank<D, 2>(a, mix, grid, threads, smem, st); break;
-            case 3: rc = launch_fused_lowrank<D, 3>(a, mix, grid, threads, smem, st); break;
-            case 4: rc = launch_fused_lowrank<D, 4>(a, mix, grid, threads, smem, st); break;
-            default: rc = launch_fused_lowrank<D, 8>(a, mix, grid, threads, smem, st); break;
-        }
+        rc = max_rank <= 1 ? launch_fused_lowrank_q<D, 1>(a, mix, grid, threads, smem, st)
+                           : launch_fused_lowrank_q<D, 2>(a, mix, grid, threads, smem, st);
     } else {
         MixB<D> mb = {};     // kernel parameter; only the first Q blocks are read
         for (int q = 0; q < a.Q; ++q)

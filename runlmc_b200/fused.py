@@ -15,6 +15,10 @@ def _dev(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _no_handle():
+    return None
+
+
 KERNEL_KINDS = {'RBF': 0, 'Matern32': 1, 'StdPeriodic': 2}   # LMC_KERN_* of include/lmc_b200.h
 
 
@@ -80,6 +84,11 @@ class FusedLMC:
         self.Q = 0
         self.shape = (self.n, self.n)
         self.dtype = np.float64
+
+    def __reduce__(self):
+        # device handles do not travel: whatever holds one (e.g. the cache gen_grid_kernel keeps on an
+        # interpolant) unpickles to None and is rebuilt on demand
+        return (_no_handle, ())
 
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
@@ -245,11 +254,22 @@ class FusedLMC:
         return out
 
     # ---- solves ----------------------------------------------------------
-    def minres(self, RHS, tol=1e-4, maxiter=None, check_every=100):
+    def diagonal(self):
+        """diag(K~) in the caller's point order (exact, without forming K~; lmc_op_diagonal)."""
+        out = np.empty(self.n)
+        nat.check(nat.lib.lmc_op_diagonal(self._h, nat.host_ptr(out)))
+        return out
+
+    def minres(self, RHS, tol=1e-4, maxiter=None, check_every=100, precond=None):
         """Batched Iterative.solve (approx/iterative.py:24-62) on the rows of
-        RHS.  Returns (X, iters, resid, istop)."""
+        RHS.  Returns (X, iters, resid, istop).  precond='jacobi': scipy's M = diag(K~)^-1."""
         RHS = self._block(RHS)
         P = RHS.shape[0]
+        if precond is not None:
+            torch = nat.require_cuda()
+            X, iters, resid, istop = self.minres_device(torch.as_tensor(RHS, device='cuda'), tol=tol, maxiter=maxiter,
+                                                        check_every=check_every, precond=precond)
+            return X.cpu().numpy(), iters, resid, istop
         X = np.empty_like(RHS)
         iters = np.zeros(P, dtype=np.int32)
         resid = np.zeros(P, dtype=np.float64)
@@ -275,17 +295,21 @@ class FusedLMC:
             nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(info)))
         return X, iters, resid, info
 
-    def minres_device(self, RHS, tol=1e-4, maxiter=None, check_every=100):
+    PRECONDITIONERS = {None: 0, 'none': 0, 'jacobi': 1}     # LMC_PRECOND_* of include/lmc_b200.h
+
+    def minres_device(self, RHS, tol=1e-4, maxiter=None, check_every=100, precond=None):
         torch = nat.require_cuda()
         assert RHS.is_cuda and RHS.dtype == torch.float64 and RHS.is_contiguous()
+        if precond not in self.PRECONDITIONERS:
+            raise ValueError('unknown preconditioner {!r}'.format(precond))
         P = RHS.shape[0]
         X = torch.empty_like(RHS)
         iters = np.zeros(P, dtype=np.int32)
         resid = np.zeros(P, dtype=np.float64)
         istop = np.zeros(P, dtype=np.int32)
-        nat.check(nat.lib.lmc_minres(
+        nat.check(nat.lib.lmc_minres_pre(
             self._h, _dev(RHS), RHS.shape[1], P, _dev(X), float(tol),
-            int(self.n if maxiter is None else maxiter), int(check_every),
+            int(self.n if maxiter is None else maxiter), int(check_every), self.PRECONDITIONERS[precond],
             nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(istop),
             nat.current_stream_ptr()))
         return X, iters, resid, istop

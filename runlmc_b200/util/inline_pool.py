@@ -27,11 +27,12 @@ def _batched_solves(f, ls):
     K0, _, _, minres0, tol0 = norm[0]
     if any(a[0] is not K0 or a[3] != minres0 or a[4] != tol0 for a in norm):
         return None
-    if getattr(K0, 'preconditioner', None) is not None or not hasattr(K0, '_apply_dev'):
+    if not hasattr(K0, '_apply_dev'):
         return None
     import numpy as np
     RHS = np.array([np.asarray(a[1], dtype=np.float64).reshape(-1) for a in norm])
-    X, iters, resid, istop = solve_block(K0, RHS, tol=tol0, minres=minres0)
+    X, iters, resid, istop = solve_block(K0, RHS, tol=tol0, minres=minres0,
+                                         preconditioner=getattr(K0, 'preconditioner', None))
     Iterative.report(K0, resid, istop, tol0, minres0)
     return [(x, int(it), float(r)) if a[2] else x for a, x, it, r in zip(norm, X, iters, resid)]
 

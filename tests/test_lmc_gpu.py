@@ -140,13 +140,151 @@ def test_iterative_solve_cg(fuse):
     assert err <= 1e-4
 
 
-def test_preconditioner_is_refused_loudly():
-    """iterative.py:47 forwards K.preconditioner to scipy; the device solvers are M = I only."""
+@pytest.mark.parametrize('name', ['A', '2d'])
+@pytest.mark.parametrize('path', ['jacobi', 'generic', 'tree'])
+def test_preconditioned_solve_matches_reference(name, path):
+    """K.preconditioner is forwarded as scipy's M (iterative.py:47-50).  Golden: the reference's own
+    Iterative.solve with K.preconditioner = Diag(1 / diag K).  Paths: the fused operator with the
+    library's Jacobi preconditioner (lmc_minres_pre), the fused operator with an arbitrary Matrix
+    preconditioner and the plain operator tree (both through lmc_minres_generic_pre)."""
     from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
-    from runlmc_b200.approx.iterative import Iterative
-    prob, _ = golden_problem('lmc_A')
+    from runlmc_b200.approx.iterative import Iterative, JacobiPreconditioner, fused_of
+    from runlmc_b200.linalg.diag import Diag
+    g = load_golden('extra')
+    prob, _ = golden_problem('lmc_' + name)
+    fk, dists, interps, ad = build(prob, fuse=path != 'tree')
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    dK = g['pre_%s_diag' % name]
+    if path == 'jacobi':
+        assert rel_err(fused_of(K).diagonal(), dK) < 1e-13
+        K.preconditioner = JacobiPreconditioner(K)
+        assert rel_err(K.preconditioner.v, 1.0 / dK) < 1e-13
+    else:
+        K.preconditioner = Diag(1.0 / dK)
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, tol=1e-4)
+    assert abs(ctr - int(g['pre_%s_ctr' % name])) <= 3
+    assert rel_err(x, g['pre_%s_x' % name]) < 1e-5
+    assert err <= max(1e-4, 3 * float(g['pre_%s_err' % name]))
+    # an indefinite M: scipy raises ValueError (minres.py:259), so does the mirror
+    K.preconditioner = Diag(-np.ones(prob.n))
+    with pytest.raises(ValueError):
+        Iterative.solve(K, prob.y)
+    K.preconditioner = Diag(1.0 / dK)
+    with pytest.raises(NotImplementedError):          # scipy's cg takes M too; the device cg does not
+        Iterative.solve(K, prob.y, minres=False)
+
+
+def test_preconditioned_iterates_match_oracle():
+    """Fixed iteration counts of the preconditioned recurrence against the oracle's restated scipy loop."""
+    from oracle import lmc_oracle as orc
+    from runlmc_b200.fused import FusedLMC
+    prob = synthetic.make_problem('d_small', seed=11, cells_per_lengthscale=6)
+    op = FusedLMC(prob.Xs, prob.grids)
+    op.set_params(prob.tops, prob.coreg_mats(), prob.noise, prob.coreg_vecs, prob.coreg_diags)
+    spec = orc.KernelSpec(['rbf'] * prob.Q, [[x] for x in prob.gammas], prob.coreg_vecs, prob.coreg_diags,
+                          prob.noise)
+    ref = orc.build_operator(spec, prob.Xs, prob.grids, rep='sum')
+    dK = ref.diagonal()
+    assert rel_err(op.diagonal(), dK) < 1e-13
+    RHS = np.vstack([prob.y[None, :], prob.probes[:4]])          # 5 columns: two pairs and an odd one
+    for k in (1, 2, 3, 7):
+        X, iters, _, istop = op.minres(RHS, tol=1e-4, maxiter=k, check_every=10 ** 6, precond='jacobi')
+        for b, x, it in zip(RHS, X, iters):
+            xr, _, itn_r, _ = orc.minres(ref.matvec, b, 1e-10, k, psolve=lambda r: r / dK)
+            assert it == itn_r
+            assert rel_err(x, xr) < 1e-10
+
+
+def test_operators_keep_their_own_parameters():
+    """Two operators built from the same interpolants share one device handle; each must keep the
+    hyper-parameters it was built with (the reference returns independent operators)."""
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import fused_of
+    prob, g = golden_problem('lmc_2d')
+    fk, dists, interps, ad = build(prob)
+    K1, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    v = g['V'][0]
+    before = K1.matvec(v)
+    assert rel_err(before, g['KV'][0]) < 1e-10
+    fk.noise = 3.0 * prob.noise                        # in place, like an optimiser step
+    fk.coreg_diags = [2.0 * k for k in prob.coreg_diags]
+    for k in fk._kernels:
+        k.inv_lengthscale = 1.7 * k.inv_lengthscale
+    K2, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    assert fused_of(K1) is fused_of(K2)                # one handle ...
+    after2 = K2.matvec(v)
+    assert rel_err(after2, before) > 1e-2
+    np.testing.assert_array_equal(K1.matvec(v), before)      # ... two parameter states
+    np.testing.assert_array_equal(K2.matvec(v), after2)
+    # and the generic tree of K1 still holds K1's values too
+    assert rel_err(K1.Ks[0].matvec(v) + K1.Ks[1].matvec(v), before) < 1e-10
+
+
+@pytest.mark.parametrize('kind', ['slfm', 'indep'])
+def test_slfm_identity_quirk_is_not_fused(kind):
+    """SLFM-only / independent-GP-only kernels with Q > 1: the reference's slfm tree carries Identity(D m)
+    for the empty part (grid_kernel.py:84-86, 101-103).  The fused operator cannot represent that, so
+    gen_grid_kernel must leave these models to the tree -- which reproduces the reference."""
+    from runlmc_b200.approx.interpolation import multi_interpolant
+    from runlmc_b200.lmc.functional_kernel import FunctionalKernel
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel, FusedSumMatrix
+    from runlmc_b200.kern import RBF
+    g = load_golden('extra')
+    prob, _ = golden_problem('lmc_2d')
+    kerns = [RBF(x) for x in prob.gammas]
+    if kind == 'slfm':
+        fk = FunctionalKernel(D=prob.D, slfm_kernels=kerns)
+    else:
+        fk = FunctionalKernel(D=prob.D, indep_gp=kerns, indep_gp_index=[q % prob.D for q in range(prob.Q)])
+    fk.noise = prob.noise
+    fk.coreg_vecs = list(g[kind + '_coreg_vecs'])
+    fk.coreg_diags = list(g[kind + '_coreg_diags'])
+    fk.set_input_dim(prob.ndim)
+    ad = tuple(range(prob.ndim))
+    W = multi_interpolant(prob.Xs, *prob.grids)
+    K, _ = gen_grid_kernel(fk, {ad: prob.dists}, {ad: (W, W.transpose().tocsr())}, prob.lens)
+    assert not isinstance(K, FusedSumMatrix)
+    for v, kv in zip(g['V'], g[kind + '_KV']):
+        assert rel_err(K.matvec(v), kv) < 1e-10
+
+
+def test_fused_operator_survives_pickling():
+    """The reference ships K to pool workers by pickling it (stochastic_deriv.py:51-52).  The device
+    handle does not travel; the unpickled operator walks its (device-backed) tree instead."""
+    import pickle
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import fused_of
+    prob, g = golden_problem('lmc_A')
     fk, dists, interps, ad = build(prob)
     K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
-    K.preconditioner = K
-    with pytest.raises(NotImplementedError):
-        Iterative.solve(K, prob.y)
+    K2 = pickle.loads(pickle.dumps(K))
+    assert fused_of(K2) is None
+    for v, kv in zip(g['V'], g['KV']):
+        assert rel_err(K2.matvec(v), kv) < 1e-10
+
+
+def test_starmap_of_solves_is_one_block_solve():
+    """The batching seam (stochastic_deriv.py:39-52): starmap(Iterative.solve, tasks) over one shared K."""
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import Iterative
+    from runlmc_b200.util.inline_pool import InlinePool
+    from runlmc_b200 import _native as nat
+    prob, g = golden_problem('lmc_B')
+    fk, dists, interps, ad = build(prob)
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    tasks = [(K, prob.y, True, True, 1e-4)] + [(K, r, False, True, 1e-4) for r in prob.probes[:3]]
+    l0 = nat.lib.lmc_launch_count()
+    one = Iterative.solve(*tasks[0])
+    per_solve = nat.lib.lmc_launch_count() - l0
+    l0 = nat.lib.lmc_launch_count()
+    out = InlinePool(None).starmap(Iterative.solve, tasks)
+    batched = nat.lib.lmc_launch_count() - l0
+    assert batched < 2 * per_solve                       # not four solves
+    x, ctr, err = out[0]
+    assert abs(ctr - int(g['solve_y_ctr'])) <= 3 and rel_err(x, g['solve_y_x']) < 1e-5
+    assert rel_err(x, one[0]) < 1e-5
+    for r, xr in zip(prob.probes[:3], out[1:]):
+        assert xr.shape == (prob.n,)
+        assert np.linalg.norm(K.matvec(xr) - r) < 1e-2
+    # anything else runs task by task
+    assert InlinePool(None).starmap(lambda a, b: a + b, [(1, 2), (3, 4)]) == [3, 7]
