@@ -41,7 +41,10 @@ UNIT = 'MVM*RHS/s'
 CPL = {'A': 4, 'B': 8, 'C': 5, 'D': 2, 'E': 1.5}     # grid cells per (shortest) lengthscale
 # hyper-parameters of the headline gradient row: kernels resolved by the grid and a noise level on which the
 # reference's stopping rule converges below tol (picked with tools/conv_probe.py)
-GRAD_PARAMS = {'E': dict(cpl=4.0, eps=1.0), 'D': dict(cpl=4.0, eps=1.0)}
+# (tools/conv_probe.py, profiles/r02_conv_probe.txt).  At n = 1M scipy's rule -- relative to ||A|| ||x|| with
+# ||b|| = 1000 -- only reaches an absolute residual of 1e-4 when kappa_2 is O(10^2): same kernels as the
+# product benchmark, noise variances scaled up (a low signal-to-noise model).
+GRAD_PARAMS = {'E': dict(cpl=1.5, eps=1.0, noise_scale=300.0), 'D': dict(cpl=2.0, eps=1.0, noise_scale=100.0)}
 
 
 def workload_desc(name, prob):
@@ -297,6 +300,14 @@ def gradient_row(op, prob, rank, world, dev, barrier, peak, label, note):
     import torch
     import torch.distributed as dist
     from runlmc_b200.distributed import sharded_gradient
+    # kappa_2 estimate: lambda_max by power iteration, lambda_min >= the smallest noise variance
+    v = torch.as_tensor(prob.probes[:1].copy(), device=dev)
+    lam = 0.0
+    for _ in range(30):
+        w = op.mvm_device(v)
+        lam = float(torch.linalg.norm(w))
+        v = (w / lam).contiguous()
+    kappa2 = lam / float(prob.noise.min())
     barrier()
     t0 = time.perf_counter()
     grads, stats = sharded_gradient(op, prob.y, prob.probes, None, prob.coreg_vecs,
@@ -316,6 +327,7 @@ def gradient_row(op, prob, rank, world, dev, barrier, peak, label, note):
             'hyperparameters': int(flat.size), 'minres_iter_rhs_per_s': it_rate,
             'lengthscales_in_grid_cells': [float(1.0 / np.sqrt(g) * (max(prob.grid_sizes) - 1)) for g in prob.gammas],
             'noise': [float(prob.noise.min()), float(prob.noise.max())],
+            'kappa2_upper_estimate': kappa2, 'lambda_max': lam,
             'gradient_l2': float(np.linalg.norm(flat)), 'gradient_checksum': float(flat.sum()),
             'gradient_values': [float(v) for v in flat],
             'includes': 'host->device copies of y/probes, N+1 MINRES solves (tol 1e-4, reference stopping rules), '
@@ -441,8 +453,6 @@ def run_own(args):
     ms = float(t.item())
     ms_step = ms / args.steps
     value = total_units * args.steps / (ms / 1e3)
-    # timed_product runs its warm-up passes inside the window: count only the timed launches
-    launches = launches * args.steps // max(1, (launches // max(1, launches // max(args.steps, 1))))
     parity = parity_check(op, ref, Vh, OUT)
     pe = torch.tensor([parity['max_rel_err_vs_oracle']], dtype=torch.float64, device=dev)
     if world > 1:
@@ -528,12 +538,13 @@ def run_own(args):
     if not args.no_grad:
         gp = GRAD_PARAMS.get(args.workload)
         if gp:
-            pc = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=gp['cpl'], eps=gp['eps'])
+            pc = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=gp['cpl'], eps=gp['eps'],
+                                        noise_scale=gp['noise_scale'])
             op.set_kernels([RBF(g) for g in pc.gammas], pc.coreg_mats(), pc.noise, pc.coreg_vecs, pc.coreg_diags)
             grad = gradient_row(op, pc, rank, world, dev, barrier, peak, 'converging',
-                                'lengthscales of %g..%g grid cells, noise ~ 1/Gamma(1 + 1/eps, 1) with eps = %g '
-                                '(the reference benchmark\'s noise parameter, benchlib/bench.py:111-115)'
-                                % (gp['cpl'], 4 * gp['cpl'], gp['eps']))
+                                'lengthscales of %g..%g grid cells, noise ~ %g / Gamma(1 + 1/eps, 1) with eps = %g '
+                                '(eps: the reference benchmark\'s noise parameter, benchlib/bench.py:111-115)'
+                                % (gp['cpl'], 4 * gp['cpl'], gp['noise_scale'], gp['eps']))
             op.set_kernels([RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
                            prob.coreg_diags)
         if not args.no_ill:

@@ -549,6 +549,7 @@ static int minres_iteration(MinresOperator& A, Preconditioner* M, MinresState& s
 
 struct GraphSet {
     cudaGraphExec_t exec[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long launches[6] = {0, 0, 0, 0, 0, 0};   // kernels inside each captured iteration
     ~GraphSet() { for (auto& e : exec) if (e) cudaGraphExecDestroy(e); }
 };
 
@@ -646,7 +647,9 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
                 // advances exactly as in the eager path)
                 cudaGraph_t g = nullptr;
                 LMC_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                const unsigned long long l0 = g_launches.load(std::memory_order_relaxed);
                 const int rc = minres_iteration(A, M, s, st);
+                graphs.launches[phase] = g_launches.load(std::memory_order_relaxed) - l0;
                 const cudaError_t e = cudaStreamEndCapture(st, &g);
                 if (rc != 0) { if (g) cudaGraphDestroy(g); return rc; }
                 LMC_CHECK(e);
@@ -658,7 +661,7 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
                 { double* t = s.r1; s.r1 = s.r2; s.r2 = s.y; s.y = t; }
                 if (M) { double* t = s.zold; s.zold = s.z; s.z = t; }
                 { double* t = s.wa; s.wa = s.wb; s.wb = s.wc; s.wc = t; }
-                count_launch(M ? 7 : 5);
+                count_launch((int)graphs.launches[phase]);   // the replayed graph runs the same kernels
             }
             LMC_CHECK(cudaGraphLaunch(graphs.exec[phase], st));
         } else {

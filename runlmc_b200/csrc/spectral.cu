@@ -515,6 +515,7 @@ __global__ void stage_twiddle_kernel(cplx* tab, int L, FftPlan pl, StageTw lay) 
 
 }  // namespace lmc
 #include "spectral_fused.cuh"
+#include "spectral_rows512.cuh"
 namespace lmc {
 LMC_FUSED_EXTERN(1) LMC_FUSED_EXTERN(2) LMC_FUSED_EXTERN(3) LMC_FUSED_EXTERN(4)
 LMC_FUSED_EXTERN(5) LMC_FUSED_EXTERN(6) LMC_FUSED_EXTERN(7) LMC_FUSED_EXTERN(8)
@@ -771,7 +772,12 @@ int SpectralEngine::spectrum_lines(const double* spec, double* specL, double* sp
             count_launch();
         }
         const long total = (long)Q * emb_.bins;
-        col512_spec_kernel<<<ceil_div(total, 256), 256, 0, st>>>(specL, specP, total);
+        // both axes 512: the row passes use the register transform too and the spectra follow its
+        // position order along the lines as well (spectral_rows512.cuh)
+        static const bool no_rows = getenv("LMC_NO_ROWS512") != nullptr || getenv("LMC_NO_COL512") != nullptr;
+        rows512_ = emb_.mt[1] == 512 && !no_rows;
+        if (rows512_) col512_spec2_kernel<<<ceil_div(total, 256), 256, 0, st>>>(specL, specP, total);
+        else col512_spec_kernel<<<ceil_div(total, 256), 256, 0, st>>>(specL, specP, total);
         count_launch();
         LMC_CHECK(cudaGetLastError());
     }
@@ -798,6 +804,53 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         LMC_CHECK(cudaGetLastError());
     }
     const cplx* stw = stage_tw_;
+    if (e.ndim == 2 && rows512_ && f.specP && D <= 16) {
+        // 512 x 512 embedding: register transforms on both axes, bulk-copy (TMA) data movement in the
+        // transposing row passes (spectral_rows512.cuh, spectral_col512.cuh)
+        const int xpitch = ceil_div(e.m[0], 8) * 8;
+        static bool attr = false;
+        if (!attr) {
+            LMC_CHECK(cudaFuncSetAttribute(rows512_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kR512SmemFwd));
+            LMC_CHECK(cudaFuncSetAttribute(rows512_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kR512SmemInv));
+            attr = true;
+        }
+        Rows512Args r = {};
+        r.G_in = G; r.G_out = G; r.ST = S;
+        r.g_slab = e.grid_pitch; r.st_slab = (long)e.mt[1] * xpitch;
+        r.mx = e.m[0]; r.my = e.m[1]; r.xpitch = xpitch; r.nslab = npairs * D;
+        r.spc = 4;
+        r.tw1 = tw512_;
+        dim3 grid((unsigned)(xpitch / 8), (unsigned)ceil_div(r.nslab, r.spc));
+        {
+            ProfScope prof(PROF_FFT_FWD_CONTIG, st);
+            rows512_fwd_kernel<<<grid, 256, kR512SmemFwd, st>>>(r);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        }
+        f.data = S;
+        f.slab_stride = r.st_slab; f.line_stride = xpitch;
+        f.n_lines = e.mt[1]; f.L = e.mt[0]; f.valid = e.m[0];
+        f.force_col512 = 1;
+        int rc = 1;
+        switch (D) {
+#define LMC_FUSED_CASE(DD) case DD: rc = launch_fused_lines<DD>(f, stw, mix, npairs, st); break;
+            LMC_FUSED_CASE(1) LMC_FUSED_CASE(2) LMC_FUSED_CASE(3) LMC_FUSED_CASE(4) LMC_FUSED_CASE(5)
+            LMC_FUSED_CASE(6) LMC_FUSED_CASE(7) LMC_FUSED_CASE(8) LMC_FUSED_CASE(9) LMC_FUSED_CASE(10)
+            LMC_FUSED_CASE(11) LMC_FUSED_CASE(12) LMC_FUSED_CASE(13) LMC_FUSED_CASE(14) LMC_FUSED_CASE(15)
+            LMC_FUSED_CASE(16)
+#undef LMC_FUSED_CASE
+        }
+        LMC_TRY(rc);
+        {
+            ProfScope prof(PROF_FFT_INV_CONTIG, st);
+            rows512_inv_kernel<<<grid, 256, kR512SmemInv, st>>>(r);
+            count_launch();
+            LMC_CHECK(cudaGetLastError());
+        }
+        return 0;
+    }
     if (e.ndim == 2) {
         const int xpitch = ceil_div(e.m[0], 8) * 8;
         RowsTArgs r = {};

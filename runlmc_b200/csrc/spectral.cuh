@@ -75,6 +75,7 @@ class SpectralEngine {
     cplx* stage_tw_rows_ = nullptr;               // same for the transposing row pass (2-D)
     cplx* stage_tw_ = nullptr;                    // per-stage twiddles of the fused kernel's line length
     cplx* tw512_ = nullptr;                       // first-stage twiddles of the 512-point column kernel
+    bool rows512_ = false;                        // both axes 512: register/bulk-copy row passes, specP ordered for them
 };
 
 // real grid vectors X[k][D*m] <-> complex pair slabs Z[ceil(k/2)][D][gpitch]

@@ -175,6 +175,7 @@ struct FusedArgs {
     int pitch, half;
     const double* specP;          // spectra in the col512 mix layout (or null)
     const cplx* tw512;            // col512 first-stage twiddles
+    int force_col512;             // the row passes already committed to the register transform's order
 };
 
 template <int D, class MIX>
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, 
 // the register/shuffle column kernel for 512-point pruned lines (spectral_col512.cuh)
 static inline bool use_col512(const FusedArgs& a) {
     static const bool off = getenv("LMC_NO_COL512") != nullptr;
-    return !off && a.L == 512 && a.half && a.specP && a.tw512 && a.valid <= 256;
+    return (a.force_col512 || !off) && a.L == 512 && a.half && a.specP && a.tw512 && a.valid <= 256;
 }
 
 template <int D, class MIX>

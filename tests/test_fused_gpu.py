@@ -47,6 +47,10 @@ PROBLEMS = {
     # multiple of 32 so the last loads/stores of a line are partially masked
     'col512': lambda: synthetic.make_problem('e_small', seed=15, cells_per_lengthscale=4,
                                              lens=[900, 800, 850], grid=[200, 12], N=6),
+    # both axes in (128, 256]: register transforms + bulk-copy (TMA) row passes (spectral_rows512.cuh); m_x not
+    # a multiple of 8 (partial last row group), m_y not a multiple of 32
+    'rows512': lambda: synthetic.make_problem('e_small', seed=17, cells_per_lengthscale=4, edge=True,
+                                              lens=[700, 0, 650], grid=[130, 200], N=6),
     'col512_edge': lambda: synthetic.make_problem('e_small', seed=16, cells_per_lengthscale=4, edge=True,
                                                   lens=[400, 0, 300, 500, 20], D=5, grid=[131, 9], N=4),
     'four_step': lambda: synthetic.make_problem('d_small', seed=14, cells_per_lengthscale=40,
@@ -105,7 +109,7 @@ def test_mvm_against_reference_golden(name):
         assert rel_err(a, b) < MVM_TOL
 
 
-@pytest.mark.parametrize('name', ['2d_small', 'd_small', 'C', 'four_step', 'col512', 'col512_edge'])
+@pytest.mark.parametrize('name', ['2d_small', 'd_small', 'C', 'four_step', 'col512', 'col512_edge', 'rows512'])
 def test_lowrank_mix_equals_dense_mix(name):
     prob = PROBLEMS[name]()
     rng = np.random.default_rng(3)

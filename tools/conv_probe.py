@@ -4,7 +4,7 @@ kernel lengthscale (grid cells) and the noise level eps (noise ~ 1 / Gamma(1 + 1
 benchmark's parameter, benchmarks/benchlib/bench.py:111-115).  Used to pick bench.py's converging
 gradient row.
 
-    python tools/conv_probe.py E 1.5,4 0.1,1 [jacobi]
+    python tools/conv_probe.py E 1.5,4 0.1,1 [jacobi|-] [noise scales]
 """
 import os
 import sys
@@ -22,11 +22,12 @@ def main():
     wl = sys.argv[1]
     cpls = [float(x) for x in sys.argv[2].split(',')]
     epss = [float(x) for x in sys.argv[3].split(',')]
-    pre = sys.argv[4] if len(sys.argv) > 4 else None
+    pre = sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != '-' else None
+    scales = [float(x) for x in sys.argv[5].split(',')] if len(sys.argv) > 5 else [1.0]
     op = None
     for cpl in cpls:
-        for eps in epss:
-            prob = synthetic.make_problem(wl, seed=1234, cells_per_lengthscale=cpl, eps=eps, N=4)
+        for eps, scale in [(e, s) for e in epss for s in scales]:
+            prob = synthetic.make_problem(wl, seed=1234, cells_per_lengthscale=cpl, eps=eps, N=4, noise_scale=scale)
             if op is None:
                 op = FusedLMC(prob.Xs, prob.grids)
             op.set_kernels([kern.RBF(g) for g in prob.gammas], prob.coreg_mats(), prob.noise, prob.coreg_vecs,
