@@ -191,6 +191,7 @@ struct InterpArgs {
     long NB;
     int nb0, nb1;
     int tiles, tiles1;
+    int extra;             // 2-D strip scatter: the odd last column rides along with the last group of pairs
 };
 
 __device__ __forceinline__ bool group_active(const InterpArgs& a, int c0, int cnt) {
@@ -524,7 +525,9 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
     Smem& s = *reinterpret_cast<Smem*>(smem_raw3);
     const int tile = blockIdx.x % a.tiles;
     const int d = blockIdx.x / a.tiles;
-    const int npairs_tot = (a.ncols + 1) >> 1;
+    // a.extra: ncols = 2 G k + 1 -- the k full groups carry the odd last column as a third accumulator of the
+    // last group (all lanes of a strip compute it, lane 0 stores it) instead of a nearly empty group of its own
+    const int npairs_tot = a.extra ? (a.ncols >> 1) : ((a.ncols + 1) >> 1);
     const int ngroups = (npairs_tot + G - 1) / G;
     const int grp0 = blockIdx.y * groups_per_cta;
     const int grp1 = min(ngroups, grp0 + groups_per_cta);
@@ -548,7 +551,8 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
     }
     // one thread per group looks at the group's activity flags (instead of every thread, every group)
     if (tid >= 64 && tid < 128 && grp0 + (tid - 64) < grp1)
-        s.live[tid - 64] = group_active(a, 2 * G * (grp0 + tid - 64), 2 * G) ? 1 : 0;
+        s.live[tid - 64] = group_active(a, 2 * G * (grp0 + tid - 64),
+                                        2 * G + ((a.extra && grp0 + tid - 64 == ngroups - 1) ? 1 : 0)) ? 1 : 0;
     __syncthreads();
     if (tid == 0) {
         s.row_off[0] = 0;
@@ -591,12 +595,14 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
     const bool interior = jx0 >= 1 && jx0 + 3 <= mx - 2 && jy >= 1 && jy <= my - 2;
     const double* vre = s.v[0] + g;
     const double* vim = s.v[1] + g;
+    const double* vex = s.v[0] + G;        // the padding slot of every staged point holds the extra column
 
     for (int grp = grp0; grp < grp1; ++grp) {
         const int col0 = 2 * G * grp;
         const bool live = s.live[grp - grp0] != 0;           // uniform over the CTA
+        const bool extra = a.extra && grp == ngroups - 1;    // uniform over the CTA
         if (live) {
-            const int ncol = min(2 * G, a.ncols - col0);
+            const int ncol = min(2 * G + (extra ? 1 : 0), a.ncols - col0);
             const double* gp = a.in + (long)col0 * a.ld;
             if (i_a < npts) stage_point_values<G, CAP>(s.v[0], i_a, gp + src_a, a.ld, ncol);
             if (i_b < npts) stage_point_values<G, CAP>(s.v[0], i_b, gp + src_b, a.ld, ncol);
@@ -606,10 +612,37 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
         __syncthreads();
         const int pair = grp * G + g;
         if (live && in_grid && pair < npairs_tot) {
-            double acc[4][2];
+            double acc[4][2], acx[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = 0.0;
-            if (interior) {
+            for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = acx[c] = 0.0;
+            if (interior && extra) {
+#pragma unroll
+                for (int aa = 0; aa < 7; ++aa) {
+                    const int* brow = &s.bin[4 * sx + aa][sy];
+                    const int ibeg = brow[0], iend = brow[4];
+                    const double* pw = &s.wx[0][0] + ibeg;
+                    const double* pwy = &s.wy[0][0] + (3 + sy) * CAP + ibeg;
+                    const double* pv = vre + ibeg * VP;
+                    const double* px = vex + ibeg * VP;
+                    const unsigned char* pby = s.by + ibeg;
+                    const unsigned char* pby_end = s.by + iend;
+#pragma unroll 2
+                    for (; pby < pby_end; ++pby, ++pw, ++pwy, pv += VP, px += VP) {
+                        const double wyv = pwy[-(int)pby[0] * CAP];
+                        const double t0 = wyv * pv[0], t1 = wyv * pv[CAP * VP], t2 = wyv * px[0];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int kx = c - aa + 3;
+                            if (kx >= 0 && kx <= 3) {
+                                const double wxv = pw[kx * CAP];
+                                acc[c][0] = fma(wxv, t0, acc[c][0]);
+                                acc[c][1] = fma(wxv, t1, acc[c][1]);
+                                acx[c] = fma(wxv, t2, acx[c]);
+                            }
+                        }
+                    }
+                }
+            } else if (interior) {
 #pragma unroll
                 for (int aa = 0; aa < 7; ++aa) {
                     // bin row 4 sx + aa: cell c of the strip takes x tap c - aa + 3 from it
@@ -647,7 +680,7 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
                     if (jx >= mx) continue;
                     const int xlo = max(jx - 2, -2), xhi = min(jx + 1, mx);
                     const int ylo = max(jy - 2, -2), yhi = min(jy + 1, my);
-                    double a0 = 0.0, a1 = 0.0;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
                     for (int ix = xlo; ix <= xhi; ++ix) {
                         const int r = ix + 2 - cx0;
                         for (int iy = ylo; iy <= yhi; ++iy) {
@@ -663,11 +696,24 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
                                 const double w = wxs * wys;
                                 a0 = fma(w, vre[i * VP], a0);
                                 a1 = fma(w, vim[i * VP], a1);
+                                if (extra) a2 = fma(w, vex[i * VP], a2);
                             }
                         }
                     }
                     acc[c][0] = a0;
                     acc[c][1] = a1;
+                    acx[c] = a2;
+                }
+            }
+            if (extra && g == 0) {
+                // the odd last column: pair slot npairs_tot, imaginary part zero
+                const int cE = 2 * npairs_tot;
+                if (!a.active || a.active[cE]) {
+                    const double sE = a.in_scale ? a.in_scale[cE] : 1.0;
+                    cplx* gpx = a.G + ((long)npairs_tot * a.D + d) * a.grid_pitch + jy;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (jx0 + c < mx) gpx[(long)(jx0 + c) * my] = make_double2(acx[c] * sE, 0.0);
                 }
             }
             const int cA = 2 * pair, cB = 2 * pair + 1;
@@ -982,7 +1028,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 // which 2-D scatter kernel a segment of RHS pairs goes through
-enum ScatterKind { SCATTER_AUTO, SCATTER_G16, SCATTER_G8, SCATTER_PAIR };
+enum ScatterKind { SCATTER_AUTO, SCATTER_G16, SCATTER_G8, SCATTER_PAIR, SCATTER_G16X, SCATTER_G8X };
 
 static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, ScatterKind kind, cudaStream_t st);
 
@@ -993,6 +1039,7 @@ static int launch_strips(const PointSet& ps, InterpArgs a, int npairs, cudaStrea
     if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }
     a.tiles1 = ceil_div(ps.m[1], TY);
     a.tiles = ceil_div(ps.m[0], TX) * a.tiles1;
+    if (a.extra) npairs -= 1;                     // the odd last column rides with the last full group
     const int ngroups = ceil_div(npairs, G);
     const long ctas1 = (long)a.tiles * ps.D;
     // all groups in one CTA (weights computed once) unless that leaves the machine underfilled
@@ -1022,7 +1069,20 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     Seg segs[3];
     int nseg = 0;
     int done = npairs / 16 * 16, rem = npairs - done;
-    if (done) segs[nseg++] = {0, done, SCATTER_G16};
+    static const bool no_extra = getenv("LMC_NO_EXTRACOL") != nullptr;
+    if ((cv.ncols & 1) && !no_extra && (rem == 1 || (rem == 9 && g8_ok)) && npairs > 1) {
+        // 16 k (+ 8) pairs and one odd column: the column rides along as a third accumulator of the last
+        // group (129 columns on one GPU, the 17 of a rank when 128 probes are sharded over 8)
+        if (rem == 1) {
+            segs[nseg++] = {0, npairs, SCATTER_G16X};
+        } else {
+            if (done) segs[nseg++] = {0, done, SCATTER_G16};
+            segs[nseg++] = {done, rem, SCATTER_G8X};
+        }
+        done = npairs; rem = 0;
+    } else if (done) {
+        segs[nseg++] = {0, done, SCATTER_G16};
+    }
     if (rem >= 3 && rem <= 10 && g8_ok) {
         // 9 or 10 pairs: the second 8-lane group (1 or 2 live lanes) reuses the CTA's staged weights,
         // which is cheaper than a separate launch of the one-pair kernel
@@ -1063,9 +1123,11 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
         if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S><<<grid, 256, sizeof(SmemS), st>>>(a);
         else to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
-    } else if (kind == SCATTER_G16) {
+    } else if (kind == SCATTER_G16 || kind == SCATTER_G16X) {
+        a.extra = kind == SCATTER_G16X;
         LMC_TRY((launch_strips<16, 8, 8, kCap16>(ps, a, npairs, st)));
-    } else if (kind == SCATTER_G8) {
+    } else if (kind == SCATTER_G8 || kind == SCATTER_G8X) {
+        a.extra = kind == SCATTER_G8X;
         LMC_TRY((launch_strips<8, 16, 8, kCap8>(ps, a, npairs, st)));
     } else {
         a.tiles1 = ceil_div(ps.m[1], kTY);

@@ -166,7 +166,9 @@ def test_wide_blocks_match_narrow_blocks_and_oracle(ndim):
     for c in (0, 65, 66, 128, 299):
         assert rel_err(narrow[c], ref.matvec(V[c])) < MVM_TOL
     perm = op.perm()
-    for P in (16, 17, 19, 40, 65, 67, 129, 300):     # 8, 9, 10, 20, 33, 34, 65, 150 pairs
+    # 8, 9, 10, 17, 20, 25, 33, 34, 65, 150 pairs; 17 / 33 / 49 / 65 / 129 columns are 8 k pairs + one odd
+    # column, which the 2-D scatter carries as a third accumulator of the last group
+    for P in (16, 17, 19, 33, 40, 49, 65, 67, 129, 300):
         wide = op.mvm_device(Vd[:P].contiguous()).cpu().numpy()
         assert rel_err(wide, narrow[:P]) < 1e-12
         assert max(rel_err(wide[c], narrow[c]) for c in range(P)) < 1e-12
@@ -177,18 +179,18 @@ def test_wide_blocks_match_narrow_blocks_and_oracle(ndim):
     assert rel_err(op.mvm(V[:67]), narrow[:67]) < 1e-12
 
 
-def test_wide_minres_matches_single_column_solves():
+@pytest.mark.parametrize('P', [35, 33])
+def test_wide_minres_matches_single_column_solves(P):
     """Columns of a wide block stop at different iterations (activity masks inside the kernels);
     every column must end where it ends when solved alone."""
     prob = well_conditioned_problem()
     op = fused_from_problem(prob)
     rng = np.random.default_rng(3)
-    P = 35
     RHS = rng.standard_normal((P, prob.n)) * np.logspace(-3, 1, P)[:, None]
     RHS[7] = 0.0
     X, iters, resid, istop = op.minres(RHS, tol=1e-4, check_every=5)
     assert len(set(iters.tolist())) > 2                     # they really stop at different times
-    for c in (0, 7, 12, 33, 34):
+    for c in (0, 7, 12, P - 2, P - 1):
         x1, it1, r1, st1 = op.minres(RHS[c:c + 1], tol=1e-4, check_every=5)
         assert it1[0] == iters[c] and st1[0] == istop[c]
         # a column shares its complex FFT with its pair partner: ulp-level cross-talk through the
@@ -197,16 +199,18 @@ def test_wide_minres_matches_single_column_solves():
     assert np.all(resid < 1e-4)
 
 
-def test_wide_minres_2d():
+@pytest.mark.parametrize('P', [37, 33, 17])
+def test_wide_minres_2d(P):
+    """P = 33 / 17: 16 / 8 pairs and an odd column that the scatter carries as a third accumulator, with
+    columns (the odd one included) stopping at different iterations."""
     prob = PROBLEMS['2d_small']()
     prob.noise = np.full(prob.D, 25.0)
     op = fused_from_problem(prob)
     _, ref = oracle_from_problem(prob)
     rng = np.random.default_rng(5)
-    P = 37
     RHS = rng.standard_normal((P, prob.n)) * np.logspace(-2, 1, P)[:, None]
     X, iters, resid, istop = op.minres(RHS, tol=1e-4, check_every=5)
-    for c in (0, 18, 35, 36):
+    for c in (0, P // 2, P - 2, P - 1):
         xr, ctr, err = orc.iterative_solve(ref.matvec, RHS[c], 1e-4, check_every=5)
         assert abs(int(iters[c]) - ctr) <= 5
         assert rel_err(X[c], xr) < SOLVE_TOL
