@@ -536,6 +536,10 @@ def run_own(args):
     # row keeps the ill-conditioned operator the block product is timed on ----
     grad = grad_ill = None
     if not args.no_grad:
+        # untimed: the solver's grow-only workspace (10 P n doubles) and its pinned flags are allocated once per
+        # model, like the operator's grid workspace during the product's warm-up
+        op.minres_device(V, tol=1e-4, maxiter=2)
+        torch.cuda.synchronize()
         gp = GRAD_PARAMS.get(args.workload)
         if gp:
             pc = synthetic.make_problem(args.workload, seed=1234, cells_per_lengthscale=gp['cpl'], eps=gp['eps'],

@@ -2,7 +2,8 @@
 """profiles/ncu_traffic.json from `ncu --page raw --csv` dumps: DRAM bytes (read + write) per RHS pair
 and kernel family.   python tools/ncu_traffic.py E=<raw.csv>:<pairs> D=<raw.csv>:<pairs> ..."""
 import csv, io, json, os, sys
-FAM = [('to_grid', 'to_grid'), ('from_grid', 'from_grid'), ('fused_lines', 'mix'),
+FAM = [('to_grid', 'to_grid'), ('from_grid', 'from_grid'), ('fused_lines', 'mix'), ('fused_col512', 'mix'),
+       ('rows512_fwd', 'fft_fwd_contig'), ('rows512_inv', 'fft_inv_contig'),
        ('fft_rows_T_kernel<0>', 'fft_fwd_contig'), ('fft_rows_T_fwd_pipe', 'fft_fwd_contig'), ('fft_rows_T_kernel<1>', 'fft_inv_contig'),
        ('fft_pass_kernel<1, 0>', 'fft_fwd_strided'), ('fft_pass_kernel<1, 1>', 'fft_inv_strided'),
        ('fft_pass_kernel<0, 0>', 'fft_fwd_contig'), ('fft_pass_kernel<0, 1>', 'fft_inv_contig'),
