@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256, 2) rows512_inv_kernel(const Rows512Args a
     const bool row_ok = x0 + w < a.mx;
     if (tid == 0) mbar_init(bar, 1);
     for (int i = tid; i < kC512Tw; i += 256) tw[i] = a.tw1[i];
+    __syncthreads();                                   // barrier object and twiddles visible to everyone
     cplx* buf = tile + w * kC512Line;
     const cplx* twl = tw + lane;
     for (int t = 0; t < cnt; ++t) {

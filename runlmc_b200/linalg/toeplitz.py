@@ -67,13 +67,12 @@ class Toeplitz(Matrix):
         return la.toeplitz(self.top)
 
     def upper_eig_bound(self):
-        # Gershgorin: largest absolute row sum (toeplitz.py:69-85)
-        abstop = np.abs(self.top)
-        totals = np.copy(abstop)
-        totals[0] = abstop.sum()
-        totals[1:] -= abstop[:0:-1]
-        totals = np.add.accumulate(totals)
-        return totals.max() * (1 + EPS * len(self.top))
+        """Gershgorin bound: the largest absolute row sum (what toeplitz.py:69-85 returns).  Row i of a
+        symmetric Toeplitz matrix holds t_i .. t_1 t_0 t_1 .. t_{n-1-i}, so its absolute sum is
+        P[i] + P[n-1-i] - |t_0| with P the prefix sums of |t|."""
+        prefix = np.cumsum(np.abs(self.top))
+        rows = prefix + prefix[::-1] - abs(self.top[0])
+        return rows.max() * (1 + EPS * len(self.top))
 
     def __str__(self):
         topstr = 'size {}'.format(len(self.top)) if len(self.top) > 10 else str(self.top)

@@ -228,53 +228,48 @@ def _device_kernels(fk, idxs, fused, dists):
     return kerns
 
 
+# ---- the three representations of the grid operator K_UU (reference grid_kernel.py:77-136) ----------------
+# grid_k: [Q_group, *grid shape] kernel values of the group's kernels, in the order of fk.active_dims[active_dim].
+
+def _bttb_of(values):
+    return BTTB(np.ravel(values), values.shape)
+
+
+def _gen_sum_grid(fk, grid_k, active_dim):
+    """sum_q B_q (x) T_q, one Kronecker term per kernel."""
+    return SumMatrix([Kronecker(NumpyMatrix(B), _bttb_of(k)) for B, k in zip(fk.coreg_mats(active_dim), grid_k)])
+
+
+def _gen_bt_grid(fk, grid_k, active_dim):
+    """D x D blocks, block (i, j) the BTTB of sum_q B_q[i, j] k_q (symmetric: built once per unordered pair)."""
+    D = fk.D
+    grid_shape = grid_k.shape[1:]
+    mixed = np.einsum('qij,qm->ijm', np.array(fk.coreg_mats(active_dim)), grid_k.reshape(len(grid_k), -1))
+    upper = {(i, j): BTTB(mixed[i, j], grid_shape) for i in range(D) for j in range(i, D)}
+    return SymmSquareBlockMatrix([[upper[min(i, j), max(i, j)] for j in range(D)] for i in range(D)])
+
+
 def _gen_slfm_grid(fk, grid_k, m, active_dim):
+    """(A* (x) I) blockdiag(T_q per coregionalisation vector) (A*^T (x) I)  +  blockdiag_d(sum_q kappa_q[d] T_q);
+    an empty part is Identity(m), as in the reference (see _try_fuse)."""
     return SumMatrix([_gen_coreg_Ks(fk, grid_k, m, active_dim), _gen_diag_Ks(fk, grid_k, m, active_dim)])
 
 
 def _gen_coreg_Ks(fk, grid_k, m, active_dim):
-    kidxs = fk.active_dims[active_dim]
-    all_coreg = [fk.coreg_vecs[i] for i in fk.filter_non_indep_idxs(kidxs)]
-    if not all_coreg:
+    vecs = [fk.coreg_vecs[q] for q in fk.filter_non_indep_idxs(fk.active_dims[active_dim])]
+    if len(vecs) == 0:
         return Identity(m)
-    ranks = [len(c) for c in all_coreg]
-    A_star = np.vstack(all_coreg).T
-    I_m = Identity(int(np.prod(grid_k.shape[1:])))
-    left = Kronecker(NumpyMatrix(A_star), I_m)
-    right = Kronecker(NumpyMatrix(A_star.T), I_m)
-    toeps = []
-    for top, r in zip(grid_k[:len(all_coreg)], ranks):
-        t = BTTB(top.ravel(), top.shape)
-        toeps.extend([t] * r)
-    return Composition([left, BlockDiag(toeps), right])
+    # the non-independent kernels come first in the group, so vecs[i] belongs to grid_k[i]
+    per_vector = [t for a, k in zip(vecs, grid_k) for t in [_bttb_of(k)] * len(a)]
+    stacked = np.vstack(vecs)                                # [sum R_q, D]
+    eye = Identity(int(np.prod(grid_k.shape[1:])))
+    return Composition([Kronecker(NumpyMatrix(stacked.T), eye), BlockDiag(per_vector),
+                        Kronecker(NumpyMatrix(stacked), eye)])
 
 
 def _gen_diag_Ks(fk, grid_k, m, active_dim):
-    if fk.num_lmc[active_dim] == 0 and fk.num_indep[active_dim] == 0:
+    if not (fk.num_lmc[active_dim] or fk.num_indep[active_dim]):
         return Identity(m)
-    kidxs = fk.active_dims[active_dim]
-    diags = np.column_stack([fk.coreg_diags[k] for k in kidxs])
-    Q = grid_k.shape[0]
-    diag_tops = diags.dot(grid_k.reshape(Q, -1))
-    return BlockDiag([BTTB(top, grid_k.shape[1:]) for top in diag_tops])
-
-
-def _gen_bt_grid(fk, grid_k, active_dim):
-    Bs = np.array(fk.coreg_mats(active_dim))
-    Q = grid_k.shape[0]
-    bt = np.tensordot(Bs, grid_k.reshape(Q, -1), axes=(0, 0))
-    sizes = grid_k.shape[1:]
-    D = fk.D
-    blocks = [[None] * D for _ in range(D)]
-    for i in range(D):
-        for j in range(i, D):
-            blocks[i][j] = blocks[j][i] = BTTB(bt[i, j], sizes)
-    return SymmSquareBlockMatrix(blocks)
-
-
-def _gen_sum_grid(fk, grid_k, active_dim):
-    Q = grid_k.shape[0]
-    tops = grid_k.reshape(Q, -1)
-    sizes = grid_k.shape[1:]
-    return SumMatrix([Kronecker(NumpyMatrix(A), BTTB(top, sizes))
-                      for A, top in zip(fk.coreg_mats(active_dim), tops)])
+    kappa = np.array([fk.coreg_diags[q] for q in fk.active_dims[active_dim]])      # [Q_group, D]
+    per_output = kappa.T.dot(grid_k.reshape(len(grid_k), -1))                       # [D, m]
+    return BlockDiag([BTTB(top, grid_k.shape[1:]) for top in per_output])

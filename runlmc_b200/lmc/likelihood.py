@@ -17,10 +17,16 @@ from ..fused import assemble_gradients
 
 
 class LMCLikelihood:
+    """Gradient families of an LMC log-likelihood in terms of dK/dtheta operators (the role of reference
+    likelihood.py:20-96).  A subclass says how a derivative of a coregionalisation matrix, of a kernel or of the
+    noise becomes an operator (`_dKdt_from_dAdt`, `_dKdts_from_dKqdts`, `_dKdt_from_dEpsdt`) and how an operator
+    becomes a scalar (`_dLdt_from_dKdt`); everything here is the chain rule over the parameter layout
+    B_q = A_q^T A_q + diag(kappa_q)."""
+
     def __init__(self, functional_kernel, Ys):
         self.functional_kernel = functional_kernel
         self.y = np.hstack(Ys)
-        self.lens = list(map(len, Ys))
+        self.lens = [len(Y) for Y in Ys]
 
     def _dKdt_from_dAdt(self, dAdt, q):
         raise NotImplementedError
@@ -37,46 +43,38 @@ class LMCLikelihood:
     def alpha(self):
         raise NotImplementedError
 
+    def _coreg_partial(self, dB, q):
+        return self._dLdt_from_dKdt(self._dKdt_from_dAdt(dB, q))
+
     def coreg_vec_gradients(self):
-        fk = self.functional_kernel
-        grads = []
-        for q, a in enumerate(fk.coreg_vecs):
-            g = np.zeros(np.shape(a))
-            for i, ai in enumerate(a):
-                for j in range(fk.D):
-                    dA = np.zeros((fk.D, fk.D))
-                    dA[j] += ai
-                    dA.T[j] += ai
-                    g[i, j] = self._dLdt_from_dKdt(self._dKdt_from_dAdt(dA, q))
-            grads.append(g)
-        return grads
+        """d/dA_q[r, j]: dB_q = e_j a_r^T + a_r e_j^T."""
+        D = self.functional_kernel.D
+        out = []
+        for q, A in enumerate(self.functional_kernel.coreg_vecs):
+            A = np.atleast_2d(A)
+            g = np.empty(A.shape)
+            for r, j in np.ndindex(*A.shape):
+                dB = np.zeros((D, D))
+                dB[j, :] += A[r]
+                dB[:, j] += A[r]
+                g[r, j] = self._coreg_partial(dB, q)
+            out.append(g)
+        return out
 
     def coreg_diags_gradients(self):
-        fk = self.functional_kernel
-        grads = []
-        for q in range(fk.Q):
-            g = np.zeros(fk.D)
-            for i in range(fk.D):
-                E = np.zeros((fk.D, fk.D))
-                E[i, i] = 1
-                g[i] = self._dLdt_from_dKdt(self._dKdt_from_dAdt(E, q))
-            grads.append(g)
-        return grads
+        """d/dkappa_q[i]: dB_q = e_i e_i^T."""
+        D, Q = self.functional_kernel.D, self.functional_kernel.Q
+        units = np.eye(D)
+        return [np.array([self._coreg_partial(np.outer(units[i], units[i]), q) for i in range(D)])
+                for q in range(Q)]
 
     def kernel_gradients(self):
-        grads = []
-        for q, A in enumerate(self.functional_kernel.coreg_mats()):
-            grads.append([self._dLdt_from_dKdt(dK) for dK in self._dKdts_from_dKqdts(A, q)])
-        return grads
+        return [[self._dLdt_from_dKdt(dK) for dK in self._dKdts_from_dKqdts(B, q)]
+                for q, B in enumerate(self.functional_kernel.coreg_mats())]
 
     def noise_gradient(self):
-        D = self.functional_kernel.D
-        g = np.zeros(D)
-        for i in range(D):
-            e = np.zeros(D)
-            e[i] = 1
-            g[i] = self._dLdt_from_dKdt(self._dKdt_from_dEpsdt(e))
-        return g
+        units = np.eye(self.functional_kernel.D)
+        return np.array([self._dLdt_from_dKdt(self._dKdt_from_dEpsdt(e)) for e in units])
 
 
 class ApproxLMCLikelihood(LMCLikelihood):
@@ -89,6 +87,9 @@ class ApproxLMCLikelihood(LMCLikelihood):
         self.deriv = deriv.generate(self.K, self.y)
         self.interpolants = interpolants
         self._fused_grads = None
+        # like the reference, everything the gradients need is fixed at construction: the handle behind K is
+        # shared by later operators with other hyper-parameters, so the Gram stage runs now, on K's own
+        self._fused()
 
     # The reference evaluates both on construction (likelihood.py:103-108); here they are evaluated
     # on first use, because with device-evaluated kernels (lmc_op_set_kernels) the fused gradient

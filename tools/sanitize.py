@@ -15,7 +15,9 @@ from runlmc_b200.fused import FusedLMC  # noqa: E402
 CASES = [('A', dict(cells_per_lengthscale=4)),
          ('d_small', dict(cells_per_lengthscale=6)),
          ('e_small', dict(cells_per_lengthscale=3)),
-         ('e_small', dict(cells_per_lengthscale=3, lens=[700, 0, 650], grid=[40, 24], edge=True))]
+         ('e_small', dict(cells_per_lengthscale=3, lens=[700, 0, 650], grid=[40, 24], edge=True)),
+         # 512 x 512 embedding: register transforms, bulk-copy (TMA) row passes, the odd-column scatter (7 columns)
+         ('e_small', dict(cells_per_lengthscale=4, lens=[300, 0, 280], grid=[130, 200], edge=True))]
 
 
 def main():
@@ -36,6 +38,7 @@ def main():
         op.from_grid_device(G)
         op.mvm(Vh[:3])
         X, it, res, _ = op.minres_device(V, tol=1e-4, maxiter=12, check_every=5)
+        op.minres_device(V, tol=1e-4, maxiter=6, check_every=5, precond='jacobi')
         op.cg(Vh[:3], tol=1e-4, maxiter=6)
         op.grad_grams_device(X[0], V[1:], X[1:], None)
         torch.cuda.synchronize()
