@@ -3,9 +3,10 @@
 `gen_grid_kernel` returns the same tree the reference builds
 (SumMatrix([GridKernel..., Diag(noise)]), grid_kernel.py:49-74) -- every node is
 a device-backed runlmc_b200.linalg class -- and, when the tree is the standard
-single-active-dimension-group SKI-LMC operator, attaches ONE fused CUDA
-operator (`_fused`) that `matvec`, `Iterative.solve` and the likelihood use
-instead of walking the tree.  sum / bt / slfm are the same matrix (except the
+SKI-LMC operator, attaches ONE fused CUDA operator per active-dimension group
+(`_fused` for the usual single group: `matvec`, `Iterative.solve` and the
+likelihood use it instead of walking the tree; `FusedGroupsSumMatrix` for
+several groups).  sum / bt / slfm are the same matrix (except the
 reference's slfm tree with an empty coreg or diag part, which is left to the
 tree, see _try_fuse); the fused operator serves all three.  The handle is shared
 by the operators built from one interpolant, each of which re-binds its own
@@ -150,6 +151,37 @@ class FusedSumMatrix(SumMatrix):
         return state
 
 
+class FusedGroupsSumMatrix(SumMatrix):
+    """SumMatrix([GridKernel_g ..., Diag(noise)]) for kernels on several active-dimension groups
+    (reference grid_kernel.py:49-74 loops over fk.active_dims): one fused device operator per group --
+    W_g (sum_{q in g} B_q (x) T_q) W_g^T, the first one carrying the noise term -- instead of one launch per
+    tree node.  Solves go through the block solver's callback path with this product."""
+
+    def __init__(self, Ks, handles, states):
+        super().__init__(Ks)
+        self._handles = handles
+        self._states = states
+
+    def _apply_dev(self, X):
+        if self._handles is None:       # unpickled
+            return super()._apply_dev(X)
+        X = X.contiguous()
+        total = None
+        for handle, state in zip(self._handles, self._states):
+            Y = state.bind(handle).mvm_device(X)
+            if total is None:
+                total = Y
+            else:
+                total += Y
+        return total
+
+    def __getstate__(self):
+        state = super().__getstate__()
+        state['_handles'] = None
+        state['_states'] = None
+        return state
+
+
 def representation(fk, active_dim):
     """The reference's selection rule (grid_kernel.py:52-64)."""
     if fk.Q == 1:
@@ -168,20 +200,21 @@ def gen_grid_kernel(fk, grid_dists, interpolants, lens_per_output):
     noise = Diag(np.repeat(fk.noise, lens_per_output))
     ls = list(grid_kerns.values())
     ls.append(noise)
-    fused = _try_fuse(fk, grid_dists, interpolants, lens_per_output)
-    if fused is not None:
-        handle, state = fused
-        state.bind(handle)
-        return FusedSumMatrix(ls, handle, state), grid_kerns
+    groups = list(fk.active_dims.keys())
+    fused = [_try_fuse(fk, grid_dists, interpolants, ad, noise_on=(i == 0)) for i, ad in enumerate(groups)]
+    if all(f is not None for f in fused):
+        if len(fused) == 1:
+            handle, state = fused[0]
+            state.bind(handle)
+            return FusedSumMatrix(ls, handle, state), grid_kerns
+        return FusedGroupsSumMatrix(ls, [h for h, _ in fused], [st for _, st in fused]), grid_kerns
     return SumMatrix(ls), grid_kerns
 
 
-def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
-    """(handle, parameter state) of one fused operator when there is a single active-dimension group
-    of 1 or 2 input dimensions and the interpolant carries its geometry, else None."""
-    if len(fk.active_dims) != 1:
-        return None
-    (active_dim,) = fk.active_dims.keys()
+def _try_fuse(fk, grid_dists, interpolants, active_dim, noise_on=True):
+    """(handle, parameter state) of the fused operator of one active-dimension group of 1 or 2 input
+    dimensions whose interpolant carries its geometry, else None.  noise_on: this group's operator carries the
+    noise term (exactly one group of a model does)."""
     W = interpolants[active_dim][0]
     geom = getattr(W, 'lmc_geometry', None)
     if geom is None or len(geom[1]) not in (1, 2) or fk.D > 16:
@@ -201,14 +234,15 @@ def _try_fuse(fk, grid_dists, interpolants, lens_per_output):
         W._lmc_fused = cache
     coreg_vecs = [fk.coreg_vecs[i] for i in idxs]
     coreg_diags = [fk.coreg_diags[i] for i in idxs]
+    noise = fk.noise if noise_on else np.zeros(fk.D)
     kerns = _device_kernels(fk, idxs, cache, grid_dists[active_dim])
     if kerns is not None:
         # per-step setup on the device: kernel values are evaluated where the spectra are computed
-        state = _ParamState([kernel_descriptor(k) for k in kerns], None, fk.coreg_mats(active_dim), fk.noise,
+        state = _ParamState([kernel_descriptor(k) for k in kerns], None, fk.coreg_mats(active_dim), noise,
                             coreg_vecs, coreg_diags)
     else:
         grid_k = fk.eval_kernels_fixed_dim(grid_dists[active_dim], active_dim)
-        state = _ParamState(None, list(grid_k), fk.coreg_mats(active_dim), fk.noise, coreg_vecs, coreg_diags)
+        state = _ParamState(None, list(grid_k), fk.coreg_mats(active_dim), noise, coreg_vecs, coreg_diags)
     return cache, state
 
 

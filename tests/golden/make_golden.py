@@ -342,6 +342,55 @@ class DuckKindKernel(DuckKernel):
         return [] if self.kind == 'indep' else list(idxs)
 
 
+class DuckGroupsKernel:
+    """LMC kernels on TWO active-dimension groups of 2-D inputs: kernels 0 and 1 see input dimension 0,
+    kernel 2 sees dimension 1 (gen_grid_kernel loops over fk.active_dims, grid_kernel.py:49-74)."""
+
+    def __init__(self, prob):
+        self.p = prob
+        self.D, self.Q = prob.D, 3
+        self.noise = prob.noise
+        self.coreg_vecs = prob.coreg_vecs
+        self.coreg_diags = prob.coreg_diags
+        self.active_dims = {(0,): [0, 1], (1,): [2]}
+        self.num_lmc = {(0,): 2, (1,): 1}
+        self.num_slfm = {(0,): 0, (1,): 0}
+        self.num_indep = {(0,): 0, (1,): 0}
+
+    def coreg_mats(self, active_dim=None):
+        mats = self.p.coreg_mats()
+        return mats if active_dim is None else [mats[q] for q in self.active_dims[active_dim]]
+
+    def total_rank(self, active_dim):
+        return sum(len(self.coreg_vecs[q]) for q in self.active_dims[active_dim])
+
+    def eval_kernels_fixed_dim(self, dists, active_dim):
+        return np.array([synthetic.rbf_top(dists, self.p.gammas[q]) for q in self.active_dims[active_dim]])
+
+    def filter_non_indep_idxs(self, idxs):
+        return list(idxs)
+
+
+def groups_case(out):
+    prob = synthetic.make_problem('e_small', seed=31, cells_per_lengthscale=3, lens=[130, 90, 110],
+                                  grid=[40, 24], N=5)
+    fk = DuckGroupsKernel(prob)
+    dists, interps = {}, {}
+    for ad, grid in (((0,), prob.grids[0]), ((1,), prob.grids[1])):
+        Xs = [X[:, ad[0]] for X in prob.Xs]
+        W = ref_interp.multi_interpolant(Xs, grid)
+        interps[ad] = (W, W.transpose().tocsr())
+        dists[ad] = grid - grid[0]
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    rs = np.random.RandomState(4)
+    V = rs.randn(3, prob.n)
+    out['groups_V'] = V
+    out['groups_KV'] = np.array([K.matvec(v) for v in V])
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, minres=True, tol=1e-4)
+    out['groups_x'], out['groups_ctr'], out['groups_err'] = x, np.array(ctr), np.array(err)
+    print('two active-dimension groups: solve callbacks', ctr, 'residual', err)
+
+
 def main_extra():
     """(1) gen_grid_kernel for SLFM-only and independent-GP-only kernels; (2) Iterative.solve with a
     K.preconditioner (forwarded to scipy as M, iterative.py:47-50): the Jacobi preconditioner
@@ -374,6 +423,7 @@ def main_extra():
         out['pre_%s_diag' % name], out['pre_%s_x' % name] = dK, x
         out['pre_%s_ctr' % name], out['pre_%s_err' % name] = np.array(ctr), np.array(err)
         print('preconditioned', name, 'callbacks', ctr, 'residual', err)
+    groups_case(out)
     np.savez_compressed(os.path.join(HERE, 'extra.npz'), **out)
 
 

@@ -248,6 +248,44 @@ def test_slfm_identity_quirk_is_not_fused(kind):
         assert rel_err(K.matvec(v), kv) < 1e-10
 
 
+@pytest.mark.parametrize('fuse', [True, False])
+def test_two_active_dimension_groups(fuse):
+    """Kernels on two groups of input dimensions (gen_grid_kernel loops over fk.active_dims,
+    grid_kernel.py:49-74): one fused device operator per group, or the plain tree; product and solve against
+    the reference's own run."""
+    from runlmc_b200.approx.interpolation import multi_interpolant
+    from runlmc_b200.approx.iterative import Iterative
+    from runlmc_b200.lmc.functional_kernel import FunctionalKernel
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel, FusedGroupsSumMatrix
+    from runlmc_b200.kern import RBF
+    g = load_golden('extra')
+    prob = synthetic.make_problem('e_small', seed=31, cells_per_lengthscale=3, lens=[130, 90, 110],
+                                  grid=[40, 24], N=5)
+    kerns = [RBF(prob.gammas[0], active_dims=[0]), RBF(prob.gammas[1], active_dims=[0]),
+             RBF(prob.gammas[2], active_dims=[1])]
+    fk = FunctionalKernel(D=prob.D, lmc_kernels=kerns, lmc_ranks=[1, 1, 1])
+    fk.noise = prob.noise
+    fk.coreg_vecs = prob.coreg_vecs
+    fk.coreg_diags = prob.coreg_diags
+    fk.set_input_dim(2)
+    assert fk.active_dims == {(0,): [0, 1], (1,): [2]}
+    dists, interps = {}, {}
+    for ad, grid in (((0,), prob.grids[0]), ((1,), prob.grids[1])):
+        W = multi_interpolant([X[:, ad[0]] for X in prob.Xs], grid)
+        if not fuse:
+            W.lmc_geometry = None
+        interps[ad] = (W, W.transpose().tocsr())
+        dists[ad] = grid - grid[0]
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    assert isinstance(K, FusedGroupsSumMatrix) == fuse
+    for v, kv in zip(g['groups_V'], g['groups_KV']):
+        assert rel_err(K.matvec(v), kv) < 1e-10
+    x, ctr, err = Iterative.solve(K, prob.y, verbose=True, tol=1e-4)
+    assert abs(ctr - int(g['groups_ctr'])) <= 3
+    assert rel_err(x, g['groups_x']) < 1e-5
+    assert err <= max(1e-4, 3 * float(g['groups_err']))
+
+
 def test_fused_operator_survives_pickling():
     """The reference ships K to pool workers by pickling it (stochastic_deriv.py:51-52).  The device
     handle does not travel; the unpickled operator walks its (device-backed) tree instead."""
