@@ -39,7 +39,7 @@ void prof_end(int cat, cudaStream_t st) {
 
 static size_t spectrum_tile_bytes() {   // pairs per spectral launch: large launches beat L2 residency (measured)
     static const char* e = getenv("LMC_SPECTRUM_TILE_MB");
-    return (e ? (size_t)atoi(e) : 1024) << 20;
+    return (e ? (size_t)atoi(e) : 1536) << 20;   // config E: all 65 pairs of a 129-column block in one launch per pass
 }
 
 int op_ensure_workspace(lmc_op* op) {

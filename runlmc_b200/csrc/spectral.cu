@@ -820,7 +820,8 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         r.G_in = G; r.G_out = G; r.ST = S;
         r.g_slab = e.grid_pitch; r.st_slab = (long)e.mt[1] * xpitch;
         r.mx = e.m[0]; r.my = e.m[1]; r.xpitch = xpitch; r.nslab = npairs * D;
-        r.spc = 4;
+        static const int spc_env = getenv("LMC_ROWS512_SPC") ? atoi(getenv("LMC_ROWS512_SPC")) : 4;
+        r.spc = std::max(1, spc_env);
         r.tw1 = tw512_;
         dim3 grid((unsigned)(xpitch / 8), (unsigned)ceil_div(r.nslab, r.spc));
         {
