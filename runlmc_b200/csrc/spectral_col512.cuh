@@ -112,6 +112,22 @@ __device__ __forceinline__ void dft16(cplx* x) {
     }
 }
 
+// x[c] *= w^c (INV: conj(w)^c), c = 1..15, with the powers built on the fly from w = W512^m (the lane's own
+// root, kept in two registers for the whole kernel): two interleaved chains (odd / even exponents, step w^2),
+// so no power is more than 8 multiplications deep.  Trades 15 shared-memory loads per transform side for 15
+// complex multiplications: the kernel is bound by the LSU data pipe (80 % busy), not by the fp64 pipe (45 %).
+template <bool INV>
+__device__ __forceinline__ void twiddle_powers(cplx* x, cplx w) {
+    const cplx w2 = cmul(w, w);
+    cplx po = w, pe = w2;      // w^1, w^2
+#pragma unroll
+    for (int c = 1; c < 16; c += 2) {
+        x[c] = INV ? cmulc(x[c], po) : cmul(x[c], po);
+        if (c + 1 < 16) x[c + 1] = INV ? cmulc(x[c + 1], pe) : cmul(x[c + 1], pe);
+        if (c + 2 < 16) { po = cmul(po, w2); pe = cmul(pe, w2); }
+    }
+}
+
 struct Col512Args {
     cplx* data;               // S_T[pair][d][line][x]
     long slab_stride;         // elements per (pair, output) slab
@@ -120,23 +136,20 @@ struct Col512Args {
     int npairs, ppc;          // RHS pairs, pairs per CTA
     int Q;
     const double* specP;      // [Q][n_lines][512] spectra in the mix layout
-    const cplx* tw1;          // [15][32]  W512^{m c}
+    const cplx* tw1;          // [32]  W512^m (the first row of the [15][32] table W512^{m c})
 };
 
 template <int D, class MIX, int MINB>
 __global__ void __launch_bounds__(32 * D, MINB) fused_col512_kernel(const Col512Args a, const MIX mb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    cplx* bufs = tw + kC512Tw;                    // [D][kC512Line]
+    cplx* bufs = reinterpret_cast<cplx*>(smem_raw);   // [D][kC512Line]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int line = blockIdx.x;
     const int c2 = lane >> 1, h = lane & 1;
     const double sgn = h ? -1.0 : 1.0;
-    for (int i = threadIdx.x; i < kC512Tw; i += 32 * D) tw[i] = a.tw1[i];
+    const cplx w1 = a.tw1[lane];                  // W512^lane
     cplx* buf = bufs + warp * kC512Line;
     cplx* bx = buf + c2 * 34 + h;                 // second-stage view: y_c[h + 2 j] at bx[2 j]
-    const cplx* twl = tw + lane;
-    __syncthreads();
     for (int pp = 0; pp < a.ppc; ++pp) {
         const long pair = (long)blockIdx.y * a.ppc + pp;
         if (pair >= a.npairs) break;              // uniform over the CTA
@@ -151,8 +164,7 @@ __global__ void __launch_bounds__(32 * D, MINB) fused_col512_kernel(const Col512
 #pragma unroll
         for (int r = 0; r < 8; ++r) x[r] = (lane + 32 * r < a.valid) ? g[32 * r] : make_double2(0.0, 0.0);
         dft16<false, true, false>(x);
-#pragma unroll
-        for (int c = 1; c < 16; ++c) x[c] = cmul(x[c], twl[(c - 1) * 32]);
+        twiddle_powers<false>(x, w1);
 #pragma unroll
         for (int c = 0; c < 16; ++c) buf[c * 34 + lane] = x[c];
         __syncwarp();
@@ -208,8 +220,7 @@ __global__ void __launch_bounds__(32 * D, MINB) fused_col512_kernel(const Col512
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 16; ++c) x[c] = buf[c * 34 + lane];
-#pragma unroll
-        for (int c = 1; c < 16; ++c) x[c] = cmulc(x[c], twl[(c - 1) * 32]);
+        twiddle_powers<true>(x, w1);
         dft16<true, false, true>(x);
 #pragma unroll
         for (int r = 0; r < 8; ++r)

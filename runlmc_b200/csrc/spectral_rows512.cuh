@@ -28,8 +28,8 @@ namespace lmc {
 static const int kR512TilePitch = 9;                         // complex elements per position in the transposed tile
 static const int kR512Tile = 512 * kR512TilePitch;           // >= 8 * kC512Line: also the 8 warps' exchange buffers
 static const int kR512In = 8 * 256;                          // staged rows (forward)
-static const size_t kR512SmemFwd = sizeof(cplx) * (size_t)(kC512Tw + kR512Tile + kR512In) + 16;
-static const size_t kR512SmemInv = sizeof(cplx) * (size_t)(kC512Tw + kR512Tile) + 16;
+static const size_t kR512SmemFwd = sizeof(cplx) * (size_t)(kR512Tile + kR512In) + 16;
+static const size_t kR512SmemInv = sizeof(cplx) * (size_t)kR512Tile + 16;
 static_assert(kR512Tile >= 8 * kC512Line, "tile must hold the exchange buffers");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -67,13 +67,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // x[a] = row[lane + 32 a], a < 8 (zero padded to 16) -> x[k2] = X[c + 16 (k2 + 16 h)], lane = 2 c + h
-__device__ __forceinline__ void warp_fft512_fwd(cplx* x, cplx* buf, const cplx* twl, int lane) {
+__device__ __forceinline__ void warp_fft512_fwd(cplx* x, cplx* buf, cplx w1, int lane) {
     const int c2 = lane >> 1, h = lane & 1;
     const double sgn = h ? -1.0 : 1.0;
     cplx* bx = buf + c2 * 34 + h;
     dft16<false, true, false>(x);
-#pragma unroll
-    for (int c = 1; c < 16; ++c) x[c] = cmul(x[c], twl[(c - 1) * 32]);
+    twiddle_powers<false>(x, w1);
 #pragma unroll
     for (int c = 0; c < 16; ++c) buf[c * 34 + lane] = x[c];
     __syncwarp();
@@ -95,7 +94,7 @@ __device__ __forceinline__ void warp_fft512_fwd(cplx* x, cplx* buf, const cplx* 
 }
 
 // mirror: x[k2] in the position layout -> x[a] = row[lane + 32 a], a < 8 (unscaled inverse)
-__device__ __forceinline__ void warp_fft512_inv(cplx* x, cplx* buf, const cplx* twl, int lane) {
+__device__ __forceinline__ void warp_fft512_inv(cplx* x, cplx* buf, cplx w1, int lane) {
     const int c2 = lane >> 1, h = lane & 1;
     const double sgn = h ? -1.0 : 1.0;
     cplx* bx = buf + c2 * 34 + h;
@@ -116,8 +115,7 @@ __device__ __forceinline__ void warp_fft512_inv(cplx* x, cplx* buf, const cplx* 
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 16; ++c) x[c] = buf[c * 34 + lane];
-#pragma unroll
-    for (int c = 1; c < 16; ++c) x[c] = cmulc(x[c], twl[(c - 1) * 32]);
+    twiddle_powers<true>(x, w1);
     dft16<true, false, true>(x);
     __syncwarp();
 }
@@ -133,8 +131,7 @@ struct Rows512Args {
 
 __global__ void __launch_bounds__(256, 2) rows512_fwd_kernel(const Rows512Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    cplx* tile = tw + kC512Tw;                         // [512][9], first the warps' exchange buffers
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);    // [512][9], first the warps' exchange buffers
     cplx* in = tile + kR512Tile;                       // [8][256]
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(in + kR512In);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -145,7 +142,7 @@ __global__ void __launch_bounds__(256, 2) rows512_fwd_kernel(const Rows512Args a
     const unsigned row_bytes = (unsigned)a.my * (unsigned)sizeof(cplx);
     const bool row_ok = w < nrows;
     if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < kC512Tw; i += 256) tw[i] = a.tw1[i];
+    const cplx w1 = a.tw1[lane];                       // W512^lane
     __syncthreads();
     if (tid == 0) {
         mbar_arrive_expect_tx(bar, row_bytes * nrows);
@@ -153,7 +150,6 @@ __global__ void __launch_bounds__(256, 2) rows512_fwd_kernel(const Rows512Args a
             bulk_g2s(in + r * 256, a.G_in + slab0 * a.g_slab + (long)(x0 + r) * a.my, row_bytes, bar);
     }
     cplx* buf = tile + w * kC512Line;
-    const cplx* twl = tw + lane;
     for (int t = 0; t < cnt; ++t) {
         const long slab = slab0 + t;
         mbar_wait(bar, t & 1);
@@ -168,7 +164,7 @@ __global__ void __launch_bounds__(256, 2) rows512_fwd_kernel(const Rows512Args a
             for (int r = 0; r < nrows; ++r)
                 bulk_g2s(in + r * 256, a.G_in + (slab + 1) * a.g_slab + (long)(x0 + r) * a.my, row_bytes, bar);
         }
-        warp_fft512_fwd(x, buf, twl, lane);
+        warp_fft512_fwd(x, buf, w1, lane);
         __syncthreads();                               // every warp is done with its exchange buffer
 #pragma unroll
         for (int k = 0; k < 16; ++k) tile[(k * 32 + lane) * kR512TilePitch + w] = x[k];
@@ -187,8 +183,7 @@ __global__ void __launch_bounds__(256, 2) rows512_fwd_kernel(const Rows512Args a
 
 __global__ void __launch_bounds__(256, 2) rows512_inv_kernel(const Rows512Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx* tw = reinterpret_cast<cplx*>(smem_raw);
-    cplx* tile = tw + kC512Tw;
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + kR512Tile);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int x0 = blockIdx.x * 8;
@@ -196,10 +191,9 @@ __global__ void __launch_bounds__(256, 2) rows512_inv_kernel(const Rows512Args a
     const int cnt = (int)min((long)a.spc, (long)a.nslab - slab0);
     const bool row_ok = x0 + w < a.mx;
     if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < kC512Tw; i += 256) tw[i] = a.tw1[i];
-    __syncthreads();                                   // barrier object and twiddles visible to everyone
+    const cplx w1 = a.tw1[lane];                       // W512^lane
+    __syncthreads();                                   // barrier object visible to everyone
     cplx* buf = tile + w * kC512Line;
-    const cplx* twl = tw + lane;
     for (int t = 0; t < cnt; ++t) {
         const long slab = slab0 + t;
         if (tid == 0) mbar_arrive_expect_tx(bar, 512u * 8u * (unsigned)sizeof(cplx));
@@ -215,7 +209,7 @@ __global__ void __launch_bounds__(256, 2) rows512_inv_kernel(const Rows512Args a
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = tile[(k * 32 + lane) * kR512TilePitch + w];
         __syncthreads();                               // every warp has its row: the tile becomes the exchange buffers
-        warp_fft512_inv(x, buf, twl, lane);
+        warp_fft512_inv(x, buf, w1, lane);
         if (row_ok) {
             cplx* g = a.G_out + slab * a.g_slab + (long)(x0 + w) * a.my + lane;
 #pragma unroll
