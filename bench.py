@@ -254,6 +254,26 @@ def ncu_traffic(workload, family, pairs_per_launch):
 
 
 # --------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs next to this rank's GPU (NVML's ideal affinity) so that the pinned
+    host buffers of the end-to-end leg are allocated on the GPU's own NUMA node instead of wherever torchrun
+    started the rank.  Returns the number of CPUs bound to, or None if the platform does not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(',')]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def rfft_bins(op):
     """Number of rfft bins m~_c of the embedding: m~_1 ... (m~_P / 2 + 1)."""
     mt = [1 << int(2 * m - 1).bit_length() for m in op.grid_sizes]
@@ -413,6 +433,7 @@ def run_own(args):
         cpu = cpu_reference_rate(prob, steps=3, warmup=1, solve_iters=8 if prob.n >= 100000 else 40, keep=True)
     ref = _CPU_OP if _CPU_OP is not None else oracle_operator(prob)
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None   # before any pinned host buffer is allocated
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from runlmc_b200 import _native as nat
@@ -582,7 +603,8 @@ def run_own(args):
                 'timing': 'CUDA events on the launching stream, max over ranks',
                 'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': io_bytes, 'd2h_bytes_per_step': io_bytes,
                         'steps': e2e_steps, 'api': 'FusedLMC.mvm_into -> lmc_mvm_host (pinned host buffers, '
-                        'chunked copy/compute/copy pipeline)', 'max_abs_diff_vs_resident': e2e_check,
+                        'chunked copy/compute/copy pipeline)', 'cpus_bound_next_to_gpu': numa,
+                        'max_abs_diff_vs_resident': e2e_check,
                         'max_rel_err_vs_oracle': e2e_parity['max_rel_err_vs_oracle']},
                 'gpu_launches': launches, 'clocks': clocks, 'parity': parity, 'roofline': roofline,
                 'roofline_mvm': roofline_mvm, 'roofline_fp64': roofline_fp64, 'kernel_families': fams,
