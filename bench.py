@@ -344,6 +344,7 @@ def gradient_row(op, prob, rank, world, dev, barrier, peak, label, note):
     return {'row': label, 'note': note, 'grad_evals_per_s': 1.0 / dt, 'seconds': dt,
             'mean_minres_iterations': stats['iterations'], 'mean_final_residual': stats['solv_error'],
             'tol': 1e-4, 'converged': bool(stats['solv_error'] < 1e-4),
+            'seconds_solves_this_rank': stats['seconds_solve'], 'seconds_gram_stage_this_rank': stats['seconds_gram_stage'],
             'hyperparameters': int(flat.size), 'minres_iter_rhs_per_s': it_rate,
             'lengthscales_in_grid_cells': [float(1.0 / np.sqrt(g) * (max(prob.grid_sizes) - 1)) for g in prob.gammas],
             'noise': [float(prob.noise.min()), float(prob.noise.max())],

@@ -122,12 +122,21 @@ __global__ void __launch_bounds__(256) output_dot_kernel(const double* __restric
     }
 }
 
-struct GradBuf {
-    void* p = nullptr;
-    ~GradBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { LMC_CHECK(cudaMalloc(&p, bytes ? bytes : 8)); return 0; }
-    template <class T> T* as() { return static_cast<T*>(p); }
+// Scratch of the Gram stage, carved out of ONE grow-only allocation owned by the operator handle: at config E
+// the stage needs ~2.3 GB (a second set of grid / spectrum slabs, two D x D cross-spectra) and allocating and
+// freeing that per gradient evaluation cost 4-6x the 16 ms its kernels take.
+struct GradArena {
+    char* base;
+    size_t cap, used = 0;
+    GradArena(void* p, size_t c) : base(static_cast<char*>(p)), cap(c) {}
+    template <class T> T* take(size_t count) {
+        const size_t bytes = (sizeof(T) * (count ? count : 1) + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return used <= cap ? p : nullptr;
+    }
 };
+static size_t arena_round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 
 static int cross_spectrum(int D, const cplx* U, const cplx* Z, long bins, int npairs, double* C,
                           int accumulate, cudaStream_t st) {
@@ -160,35 +169,52 @@ int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* R
     LMC_REQUIRE(ld >= n, "leading dimension < n");
     const int DD = D * D;
 
+    // one arena for everything below (grow-only, kept in the handle between evaluations)
+    const int tile = op->tile_pairs;
+    const int nblk = ceil_div(bins, 2048);
+    const int nb2 = 64;
+    const size_t need = arena_round(sizeof(double) * (size_t)T * bins) + arena_round(sizeof(cplx) * (size_t)bins) +
+                        arena_round(sizeof(double) * (size_t)std::max(ntops_extra, 1) * cells) +
+                        arena_round(sizeof(cplx) * (size_t)tile * D * op->emb.grid_pitch) +
+                        arena_round(sizeof(cplx) * (size_t)tile * D * bins) +
+                        2 * arena_round(sizeof(double) * (size_t)DD * bins) +
+                        arena_round(sizeof(double) * (size_t)T * DD * nblk) +
+                        arena_round(sizeof(double) * (size_t)(2 * T * DD + 2 * D)) +
+                        arena_round(sizeof(double) * (size_t)D * nb2) + 4096;
+    if (need > op->grad_ws_cap) {
+        cudaFree(op->grad_ws);
+        op->grad_ws = nullptr; op->grad_ws_cap = 0;
+        LMC_CHECK(cudaMalloc(&op->grad_ws, need));
+        op->grad_ws_cap = need;
+    }
+    GradArena arena(op->grad_ws, op->grad_ws_cap);
+
     // spectra of all tops: the Q kernels already live in op->spec; derivative tops are transformed here
-    GradBuf specb, topb, workb;
-    LMC_TRY(specb.alloc(sizeof(double) * (size_t)T * bins));
-    double* spec = specb.as<double>();
+    double* spec = arena.take<double>((size_t)T * bins);
     LMC_CHECK(cudaMemcpyAsync(spec, op->spec, sizeof(double) * (size_t)Q * bins, cudaMemcpyDeviceToDevice, st));
     if (ntops_extra) {
-        LMC_TRY(workb.alloc(sizeof(cplx) * (size_t)bins));
+        cplx* work = arena.take<cplx>((size_t)bins);
         const double* tops_dev = tops_extra;   // derivative tops evaluated on the device (setup.cu) ...
         if (!extra_on_device) {                // ... or uploaded by the caller
-            LMC_TRY(topb.alloc(sizeof(double) * (size_t)ntops_extra * cells));
-            LMC_CHECK(cudaMemcpyAsync(topb.p, tops_extra, sizeof(double) * (size_t)ntops_extra * cells,
+            double* topb = arena.take<double>((size_t)ntops_extra * cells);
+            LMC_CHECK(cudaMemcpyAsync(topb, tops_extra, sizeof(double) * (size_t)ntops_extra * cells,
                                       cudaMemcpyHostToDevice, st));
-            tops_dev = topb.as<double>();
+            tops_dev = topb;
         }
         for (int t = 0; t < ntops_extra; ++t)
-            LMC_TRY(op->eng.spectrum(tops_dev + (size_t)t * cells, spec + (size_t)(Q + t) * bins,
-                                     workb.as<cplx>(), st));
+            LMC_TRY(op->eng.spectrum(tops_dev + (size_t)t * cells, spec + (size_t)(Q + t) * bins, work, st));
     }
 
     // second set of grid / spectrum slabs for the z side
-    const int tile = op->tile_pairs;
-    GradBuf g2b, s2b, cq, ct;
-    LMC_TRY(g2b.alloc(sizeof(cplx) * (size_t)tile * D * op->emb.grid_pitch));
-    LMC_CHECK(cudaMemsetAsync(g2b.p, 0, sizeof(cplx) * (size_t)tile * D * op->emb.grid_pitch, st));
-    LMC_TRY(s2b.alloc(sizeof(cplx) * (size_t)tile * D * bins));
-    LMC_TRY(cq.alloc(sizeof(double) * (size_t)DD * bins));
-    LMC_TRY(ct.alloc(sizeof(double) * (size_t)DD * bins));
-    cplx* G2 = g2b.as<cplx>();
-    cplx* S2 = s2b.as<cplx>();
+    cplx* G2 = arena.take<cplx>((size_t)tile * D * op->emb.grid_pitch);
+    LMC_CHECK(cudaMemsetAsync(G2, 0, sizeof(cplx) * (size_t)tile * D * op->emb.grid_pitch, st));
+    cplx* S2 = arena.take<cplx>((size_t)tile * D * bins);
+    double* cq = arena.take<double>((size_t)DD * bins);
+    double* ct = arena.take<double>((size_t)DD * bins);
+    double* part = arena.take<double>((size_t)T * DD * nblk);
+    double* out = arena.take<double>((size_t)(2 * T * DD + 2 * D));
+    double* pn = arena.take<double>((size_t)D * nb2);
+    LMC_REQUIRE(pn != nullptr, "internal: gradient scratch arena too small");
 
     // quadratic term: u = z = alpha (one "pair" with zero imaginary part)
     ColumnView cv;
@@ -196,11 +222,11 @@ int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* R
     cv.in = alpha; cv.ncols = 1;
     LMC_TRY(to_grid(op->ps, cv, op->G, st));
     LMC_TRY(op->eng.forward(op->G, op->S, D, st));
-    LMC_TRY(cross_spectrum(D, op->S, op->S, bins, 1, cq.as<double>(), 0, st));
+    LMC_TRY(cross_spectrum(D, op->S, op->S, bins, 1, cq, 0, st));
 
     // trace term: pairs of probes
     const int npairs = (N + 1) / 2;
-    if (npairs == 0) LMC_CHECK(cudaMemsetAsync(ct.p, 0, sizeof(double) * (size_t)DD * bins, st));
+    if (npairs == 0) LMC_CHECK(cudaMemsetAsync(ct, 0, sizeof(double) * (size_t)DD * bins, st));
     for (int p0 = 0; p0 < npairs; p0 += tile) {
         const int cnt = std::min(tile, npairs - p0);
         const int c0 = 2 * p0;
@@ -211,35 +237,23 @@ int grad_grams(lmc_op* op, const double* alpha, const double* R, const double* R
         cv.in = R + (long)c0 * ld;
         LMC_TRY(to_grid(op->ps, cv, G2, st));
         LMC_TRY(op->eng.forward(G2, S2, cnt * D, st));
-        LMC_TRY(cross_spectrum(D, op->S, S2, bins, cnt, ct.as<double>(), p0 > 0 ? 1 : 0, st));
+        LMC_TRY(cross_spectrum(D, op->S, S2, bins, cnt, ct, p0 > 0 ? 1 : 0, st));
     }
 
     // contract with every spectrum
-    const int nblk = ceil_div(bins, 2048);
-    GradBuf partb, outb;
-    LMC_TRY(partb.alloc(sizeof(double) * (size_t)T * DD * nblk));
-    LMC_TRY(outb.alloc(sizeof(double) * (size_t)(2 * T * DD + 2 * D)));
-    double* out = outb.as<double>();
     for (int which = 0; which < 2; ++which) {
-        const double* C = which ? ct.as<double>() : cq.as<double>();
-        contract_kernel<<<dim3((unsigned)nblk, (unsigned)DD), 256, 0, st>>>(C, spec, bins, T,
-                                                                           partb.as<double>(), nblk);
-        final_sum_kernel<<<ceil_div(T * DD, 128), 128, 0, st>>>(partb.as<double>(), nblk, T * DD,
-                                                              out + (size_t)which * T * DD);
+        const double* C = which ? ct : cq;
+        contract_kernel<<<dim3((unsigned)nblk, (unsigned)DD), 256, 0, st>>>(C, spec, bins, T, part, nblk);
+        final_sum_kernel<<<ceil_div(T * DD, 128), 128, 0, st>>>(part, nblk, T * DD, out + (size_t)which * T * DD);
         count_launch(2);
     }
     // noise terms
     {
-        const int nb2 = 64;
-        GradBuf pn;
-        LMC_TRY(pn.alloc(sizeof(double) * (size_t)D * nb2));
-        output_dot_kernel<<<dim3(nb2, (unsigned)D), 256, 0, st>>>(alpha, alpha, ld, 1, op->ps.out_start_dev,
-                                                                  pn.as<double>(), nb2);
-        final_sum_kernel<<<1, 128, 0, st>>>(pn.as<double>(), nb2, D, out + (size_t)2 * T * DD);
+        output_dot_kernel<<<dim3(nb2, (unsigned)D), 256, 0, st>>>(alpha, alpha, ld, 1, op->ps.out_start_dev, pn, nb2);
+        final_sum_kernel<<<1, 128, 0, st>>>(pn, nb2, D, out + (size_t)2 * T * DD);
         if (N > 0) {
-            output_dot_kernel<<<dim3(nb2, (unsigned)D), 256, 0, st>>>(RINV, R, ld, N, op->ps.out_start_dev,
-                                                                      pn.as<double>(), nb2);
-            final_sum_kernel<<<1, 128, 0, st>>>(pn.as<double>(), nb2, D, out + (size_t)2 * T * DD + D);
+            output_dot_kernel<<<dim3(nb2, (unsigned)D), 256, 0, st>>>(RINV, R, ld, N, op->ps.out_start_dev, pn, nb2);
+            final_sum_kernel<<<1, 128, 0, st>>>(pn, nb2, D, out + (size_t)2 * T * DD + D);
         } else {
             LMC_CHECK(cudaMemsetAsync(out + (size_t)2 * T * DD + D, 0, sizeof(double) * D, st));
         }

@@ -154,6 +154,7 @@ lmc_op::~lmc_op() {
     cudaFree(S);
     cudaFree(Vs);
     cudaFree(solver_ws);
+    cudaFree(grad_ws);
     cudaFree(jacobi);
 }
 

@@ -60,6 +60,8 @@ struct lmc_op {
     void* solver_ws = nullptr;
     size_t solver_ws_cap = 0;
     lmc::SolverHost solver_host;
+    void* grad_ws = nullptr;       // scratch of the gradient Gram stage (grad.cu), grow-only
+    size_t grad_ws_cap = 0;
     double* jacobi = nullptr;      // [n] 1 / diag(K~) in sorted order, valid for the current parameters if jacobi_valid
     bool jacobi_valid = false;
     double t16[64 * 16] = {0};     // top_q at the offsets (0..3, 0..3) a cubic stencil spans, per kernel (Q <= 64)

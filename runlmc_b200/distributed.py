@@ -62,17 +62,23 @@ def sharded_gradient(fused, y, probes, kernel_grad_tops, coreg_vecs, coreg_mats,
     RHS[0].copy_(torch.as_tensor(np.ascontiguousarray(y, dtype=np.float64).reshape(-1)))
     if len(local):
         RHS[1:].copy_(torch.as_tensor(np.ascontiguousarray(local)))
-    X, iters, resid, _ = fused.minres_device(RHS, tol=tol)
+    import time
+    t0 = time.perf_counter()
+    X, iters, resid, _ = fused.minres_device(RHS, tol=tol)      # returns after the solver's stream has drained
+    t_solve = time.perf_counter() - t0
     if kernel_grad_tops is None:      # derivative tops of the kernels given to set_kernels, on the device
         extra, counts = None, fused.kernel_param_counts
     else:
         extra, counts = [t for ts in kernel_grad_tops for t in ts], [len(t) for t in kernel_grad_tops]
+    t0 = time.perf_counter()
     quad, trace, nquad, ntrace = fused.grad_grams_device(
-        X[0], RHS[1:] if len(local) else None, X[1:] if len(local) else None, extra)
+        X[0], RHS[1:] if len(local) else None, X[1:] if len(local) else None, extra)    # host results: synchronous
+    t_gram = time.perf_counter() - t0
     alpha = X[0].cpu().numpy()
     it_sum = float(np.sum(iters[1:])) + (float(iters[0]) if rank == 0 else 0.0)
     rs_sum = float(np.sum(resid[1:])) + (float(resid[0]) if rank == 0 else 0.0)
     trace, ntrace, it_sum, rs_sum = allreduce_trace(trace, ntrace, it_sum, rs_sum, group)
     grads = assemble_gradients(coreg_vecs, coreg_mats, counts, N, quad, trace, nquad, ntrace)
-    stats = {'iterations': it_sum / (N + 1), 'solv_error': rs_sum / (N + 1), 'alpha': alpha}
+    stats = {'iterations': it_sum / (N + 1), 'solv_error': rs_sum / (N + 1), 'alpha': alpha,
+             'seconds_solve': t_solve, 'seconds_gram_stage': t_gram}
     return grads, stats
