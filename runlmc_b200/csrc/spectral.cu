@@ -793,6 +793,8 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
     f.specL = specL;
     f.specP = col512() ? specP : nullptr;
     f.tw512 = tw512_;
+    f.tw_plain = tw_[0];          // exp(-2 pi i k / mt[0]): every fused line length divides mt[0]
+    f.tw_n = tw_n_[0];
     // stage twiddle table of the fused kernel's line length (built on first use)
     const int Lf = e.ndim == 2 ? e.mt[0] : e.L2;
     if (!stage_tw_) {

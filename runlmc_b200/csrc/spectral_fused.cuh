@@ -176,6 +176,9 @@ struct FusedArgs {
     const double* specP;          // spectra in the col512 mix layout (or null)
     const cplx* tw512;            // col512 first-stage twiddles
     int force_col512;             // the row passes already committed to the register transform's order
+    const cplx* tw_plain;         // exp(-2 pi i k / tw_n), k < tw_n, L | tw_n (block-cooperative variant)
+    int tw_n;
+    int block_variant;            // few long lines: one CTA per line set instead of one warp per line
 };
 
 template <int D, class MIX>
@@ -227,6 +230,48 @@ __global__ void __launch_bounds__(320, 2) fused_lines_kernel(const FusedArgs a, 
 }
 
 
+// Few, long lines (the launch-bound configs A / B / C: 16-120 lines in the whole launch): one warp per line
+// leaves the GPU with a few dozen warps on a chain of dependent shared-memory stages.  This variant gives every
+// line set (the D lines of one frequency row / 1-D grid of one RHS pair) a whole CTA: block-wide radix stages
+// (fft_tile_forward / fft_tile_inverse, fft.cuh), same plan and therefore the same frequency order as the
+// warp-per-line kernel, same mix.
+template <int D, class MIX>
+__global__ void __launch_bounds__(256) fused_lines_block_kernel(const FusedArgs a, const MIX mb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);           // [D][pitch]
+    const int L = a.L, pitch = a.pitch;
+    const int line = blockIdx.x;
+    const long pair = blockIdx.y;
+    cplx* base = a.data + pair * D * a.slab_stride + (long)line * a.line_stride;
+    const int cnt = a.half ? (L >> 1) : L;                    // the upper half is known zero / not wanted
+    for (int idx = threadIdx.x; idx < cnt * D; idx += blockDim.x) {
+        const int d = idx / cnt, e = idx - d * cnt;
+        tile[d * pitch + pad_idx(e)] = e < a.valid ? base[d * a.slab_stride + e] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    fft_tile_forward(tile, pitch, D, L, a.plan, a.half != 0, a.tw_plain, a.tw_n);
+    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+        cplx* col = tile + pad_idx(p);
+        cplx x[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = col[d * pitch];
+        double f[MIX::NQ];
+        const double* sp = a.specL + (long)line * L + p;
+        const long qstride = (long)a.n_lines * L;
+#pragma unroll
+        for (int q = 0; q < MIX::NQ; ++q) f[q] = (MIX::NQ <= 4 || q < a.Q) ? __ldg(sp + q * qstride) : 0.0;
+        mb.apply(f, a.Q, x);
+#pragma unroll
+        for (int d = 0; d < D; ++d) col[d * pitch] = x[d];
+    }
+    __syncthreads();
+    fft_tile_inverse(tile, pitch, D, L, a.plan, a.half != 0, a.tw_plain, a.tw_n);
+    for (int idx = threadIdx.x; idx < cnt * D; idx += blockDim.x) {
+        const int d = idx / cnt, e = idx - d * cnt;
+        if (e < a.valid) base[d * a.slab_stride + e] = tile[d * pitch + pad_idx(e)];
+    }
+}
+
 // the register/shuffle column kernel for 512-point pruned lines (spectral_col512.cuh)
 static inline bool use_col512(const FusedArgs& a) {
     static const bool off = getenv("LMC_NO_COL512") != nullptr;
@@ -259,6 +304,17 @@ template <int D, class MIX>
 static int launch_fused_kernel(const FusedArgs& a, const MIX& m, dim3 grid, int threads, size_t smem,
                                cudaStream_t st) {
     if (use_col512(a)) return launch_col512_kernel<D, MIX>(a, m, (int)grid.y, st);
+    if (a.block_variant) {
+        static bool attr_b = false;
+        if (!attr_b) {
+            LMC_CHECK(cudaFuncSetAttribute(fused_lines_block_kernel<D, MIX>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemMax));
+            attr_b = true;
+        }
+        const size_t smem_b = (size_t)D * a.pitch * sizeof(cplx);
+        fused_lines_block_kernel<D, MIX><<<dim3((unsigned)a.n_lines, grid.y), 256, smem_b, st>>>(a, m);
+        return 0;
+    }
     static bool attr = false;
     if (!attr) {
         LMC_CHECK(cudaFuncSetAttribute(fused_lines_kernel<D, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -313,6 +369,11 @@ int launch_fused_lines(FusedArgs a, const cplx* stage_tw, const MixSpec& mix, in
     a.pitch = line_pitch(a.L);
     a.half = (a.L >= 2 && a.valid <= a.L / 2) ? 1 : 0;
     const size_t per_set = (size_t)D * a.pitch * sizeof(cplx);
+    static const bool no_block = getenv("LMC_NO_BLOCK_LINES") != nullptr;
+    // measured (B200, MINRES iteration): L = 2048 (config B) 0.078 -> 0.067 ms; L = 512 with 13 outputs (config C)
+    // and L = 256 (config A) gain nothing, so only long lines take it
+    a.block_variant = (!no_block && a.tw_plain && a.L >= 1024 && per_set <= kFusedSmemMax &&
+                       (long)a.n_lines * npairs * D <= 148L * 4) ? 1 : 0;
     int lpc = (int)std::max<size_t>(1, std::min<size_t>(48 * 1024 / per_set, (size_t)(4096 / (D * a.L) + 1)));
     lpc = std::max(1, std::min(lpc, a.n_lines));
     a.lpc = lpc;
