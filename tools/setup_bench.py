@@ -48,5 +48,45 @@ def main():
     print('%s per-step setup: host tops + upload %.2f ms, device tops %.2f ms' % (name, tp * 1e3, tk * 1e3))
 
 
+def reference_call_sequence(name='E'):
+    """The reference's own set-up sequence (interpolated_llgp.py:431-437, 192-207) through the mirror:
+    multi_interpolant -> transpose().tocsr() -> gen_grid_kernel, first call (point sort on the device) and a later
+    call with new hyper-parameters (the per-step cost).  The CSR is lazy: nothing here assembles its 4^d n entries."""
+    from runlmc_b200.approx.interpolation import multi_interpolant
+    from runlmc_b200.lmc.functional_kernel import FunctionalKernel
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    prob = synthetic.make_problem(name, seed=1234, cells_per_lengthscale={'E': 1.5, 'D': 2}.get(name, 4))
+    fk = FunctionalKernel(D=prob.D, lmc_kernels=[kern.RBF(g) for g in prob.gammas], lmc_ranks=[1] * prob.Q)
+    fk.noise = prob.noise
+    fk.coreg_vecs = prob.coreg_vecs
+    fk.coreg_diags = prob.coreg_diags
+    fk.set_input_dim(prob.ndim)
+    ad = tuple(range(prob.ndim))
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    W = multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    t_w = time.perf_counter() - t
+    t = time.perf_counter()
+    K, _ = gen_grid_kernel(fk, {ad: prob.dists}, {ad: (W, WT)}, prob.lens)
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t
+    fk.noise = 1.1 * prob.noise
+    t = time.perf_counter()
+    K2, _ = gen_grid_kernel(fk, {ad: prob.dists}, {ad: (W, WT)}, prob.lens)
+    torch.cuda.synchronize()
+    t_step = time.perf_counter() - t
+    v = np.ones(prob.n)
+    K2.matvec(v)
+    print('%s reference call sequence: multi_interpolant + transpose().tocsr() %.1f ms (CSR assembled: %s), '
+          'gen_grid_kernel first call %.1f ms, per step %.2f ms' % (
+              name, t_w * 1e3, W.materialized, t_first * 1e3, t_step * 1e3))
+    t = time.perf_counter()
+    _ = W.nnz
+    print('%s   (assembling the CSR when something does read it: %.2f s, %d nonzeros)' % (
+        name, time.perf_counter() - t, W.nnz))
+
+
 if __name__ == '__main__':
     main()
+    reference_call_sequence(sys.argv[1] if len(sys.argv) > 1 else 'E')
