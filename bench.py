@@ -202,7 +202,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------
 # roofline bookkeeping (DESIGN.md "Algorithmic bytes")
 # --------------------------------------------------------------------------
-def family_bytes(family, prob, P, bins, gpitch):
+def family_bytes(family, prob, P, bins, gpitch, rows=False):
     """Algorithmic HBM bytes of one step for a kernel family: the vectors and
     coordinates a stage must read/write plus its grid-side slabs once in and once out."""
     n, d, D = prob.n, prob.ndim, prob.D
@@ -211,7 +211,11 @@ def family_bytes(family, prob, P, bins, gpitch):
     if family == 'to_grid':
         return 8.0 * n * P + 8.0 * d * n + slab * gpitch
     if family == 'from_grid':
-        return 16.0 * n * P + 8.0 * d * n + slab * gpitch
+        # point-major blocks: the noise term moves to the transposing pass, the gather only writes
+        return (8.0 if rows else 16.0) * n * P + 8.0 * d * n + slab * gpitch
+    if family == 'other' and rows:
+        # one transposing pass: sorted column-major result + the caller's rows of X in, rows of Y out
+        return 24.0 * n * P + 4.0 * n
     if family == 'other':
         # the two permutation passes of the caller-order product (caller -> sorted before the scatter,
         # sorted -> caller after the gather): each reads and writes the block once, plus the index
@@ -295,12 +299,12 @@ def parity_check(op, ref, Vh, OUT, tol=1e-10):
             'oracle': 'oracle/lmc_oracle.py (numpy/scipy restatement pinned to the reference)'}
 
 
-def timed_product(op, V, OUT, steps, warmup, barrier, min_warm_s=0.5):
+def timed_product(product, steps, warmup, barrier, min_warm_s=0.5):
     import torch
     t_w = time.time()
     while True:                                   # warm-up: >= W steps and long enough for the clocks to settle
         for _ in range(warmup):
-            op.mvm_device(V, OUT)
+            product()
         torch.cuda.synchronize()
         if time.time() - t_w > min_warm_s:
             break
@@ -308,7 +312,7 @@ def timed_product(op, V, OUT, steps, warmup, barrier, min_warm_s=0.5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        op.mvm_device(V, OUT)
+        product()
     e1.record()
     barrier()
     return e0.elapsed_time(e1)
@@ -453,6 +457,25 @@ def run_own(args):
     V = torch.as_tensor(Vh, device=dev)
     OUT = torch.empty_like(V)
     total_units = prob.N + 1
+    # The timed block is the [n, P] argument of the reference's Matrix.matmat as numpy lays it out (C order,
+    # point-major: lmc_mvm_rows); --layout cols times P contiguous columns instead (lmc_mvm).  Both are in the
+    # caller's point order and both are reported.
+    if args.layout == 'rows':
+        X = V.t().contiguous()
+        Y = torch.empty_like(X)
+        OUT_cols = Y.t()                      # view: column c of the block
+
+        def product():
+            op.matmat_device(X, Y)
+
+        def other():
+            op.mvm_device(V, OUT)
+    else:
+        OUT_cols = OUT
+
+        def product():
+            op.mvm_device(V, OUT)
+        other = None
 
     def barrier():
         if world > 1:
@@ -462,11 +485,11 @@ def run_own(args):
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
-        op.mvm_device(V, OUT)
+        product()
     torch.cuda.synchronize()
     l0 = nat.lib.lmc_launch_count()
     sampler.window[0] = time.time()
-    ms = timed_product(op, V, OUT, args.steps, args.warmup, barrier)
+    ms = timed_product(product, args.steps, args.warmup, barrier)
     sampler.window[1] = time.time()
     launches = int(nat.lib.lmc_launch_count() - l0)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -475,7 +498,7 @@ def run_own(args):
     ms = float(t.item())
     ms_step = ms / args.steps
     value = total_units * args.steps / (ms / 1e3)
-    parity = parity_check(op, ref, Vh, OUT)
+    parity = parity_check(op, ref, Vh, OUT_cols)
     pe = torch.tensor([parity['max_rel_err_vs_oracle']], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(pe, op=dist.ReduceOp.MAX)
@@ -483,6 +506,17 @@ def run_own(args):
     parity['ok'] = parity['max_rel_err_vs_oracle'] <= parity['tolerance']
     parity['config'] = args.workload
     parity['note'] = 'columns of every rank\'s shard of the timed block, max over ranks'
+    layouts = {'timed': 'point-major [n, P] (lmc_mvm_rows)' if args.layout == 'rows' else 'P columns (lmc_mvm)',
+               'ms_per_step': ms_step}
+    if other is not None:
+        other_steps = max(3, args.steps // 2)
+        t = torch.tensor([timed_product(other, other_steps, 3, barrier, min_warm_s=0.1)], dtype=torch.float64,
+                         device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        layouts['column_major_ms_per_step'] = float(t.item()) / other_steps
+        layouts['column_major_value'] = total_units * other_steps / (float(t.item()) / 1e3)
+        layouts['max_abs_diff_between_layouts'] = float((OUT - OUT_cols).abs().max().item())
 
     # ---- end to end through host buffers: the public host API FusedLMC.mvm_into (C ABI
     # lmc_mvm_host) on pinned buffers; H2D copy of V and D2H copy of K~V are inside the timed
@@ -504,7 +538,7 @@ def run_own(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = total_units * e2e_steps / (float(t.item()) / 1e3)
-    e2e_check = float(np.abs(Opn - OUT.cpu().numpy()).max())
+    e2e_check = float(np.abs(Opn - OUT_cols.cpu().numpy()).max())
     e2e_parity = parity_check(op, ref, Vh, torch.as_tensor(Opn))
     clocks = sampler.summary()
     cnt = torch.tensor([float(P)], dtype=torch.float64, device=dev)
@@ -516,7 +550,7 @@ def run_own(args):
     l1 = nat.lib.lmc_launch_count()
     nat.profile_begin()
     for _ in range(args.steps):
-        op.mvm_device(V, OUT)
+        product()
     prof = nat.profile_end()
     launches = int(nat.lib.lmc_launch_count() - l1)          # kernels of exactly `steps` products
     bins, gpitch = nat.lib.lmc_op_embed_bins(op._h), nat.lib.lmc_op_grid_cells(op._h)
@@ -524,7 +558,7 @@ def run_own(args):
     tot = sum(v[0] for v in prof.values()) or 1.0
     fams = []
     for k, (m_, c_) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        b = family_bytes(k, prob, P, bins, gpitch)
+        b = family_bytes(k, prob, P, bins, gpitch, rows=args.layout == 'rows')
         fams.append({'family': k, 'ms_per_step': m_ / args.steps, 'launches_per_step': c_ // args.steps,
                      'share': m_ / tot, 'alg_gb_per_step': b / 1e9,
                      'alg_gbs': b / (m_ / args.steps) / 1e6 if m_ else None})
@@ -607,7 +641,8 @@ def run_own(args):
                         'chunked copy/compute/copy pipeline)', 'cpus_bound_next_to_gpu': numa,
                         'max_abs_diff_vs_resident': e2e_check,
                         'max_rel_err_vs_oracle': e2e_parity['max_rel_err_vs_oracle']},
-                'gpu_launches': launches, 'clocks': clocks, 'parity': parity, 'roofline': roofline,
+                'gpu_launches': launches, 'clocks': clocks, 'parity': parity, 'layouts': layouts,
+                'roofline': roofline,
                 'roofline_mvm': roofline_mvm, 'roofline_fp64': roofline_fp64, 'kernel_families': fams,
                 'gradient': grad, 'gradient_ill_conditioned': grad_ill, 'configs': extra}
         if cpu is not None:
@@ -641,6 +676,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--workload', default='E', choices=sorted(CPL))
+    ap.add_argument('--layout', default='rows', choices=['rows', 'cols'],
+                    help='timed block: point-major [n, P] (numpy C order of the matmat argument) or P columns')
     ap.add_argument('--no-grad', action='store_true', help='skip the gradient-evaluation leg')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-ill', action='store_true', help='skip the ill-conditioned gradient row')

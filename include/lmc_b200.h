@@ -114,6 +114,14 @@ int lmc_mvm_host(lmc_op* op, const double* V_host, long ld, int P, double* OUT_h
  * element i is point lmc_op_perm()[i] of the caller).  This is the layout the batched solver
  * keeps its state in; every access is then coalesced.                                          */
 int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_dev, void* stream);
+/* Same product on a point-major block: X[i * ldx + c], Y[i * ldy + c] for point i (caller's order) and
+ * column c < P -- numpy's C order for the [n, P] argument of Matrix.matmat (linalg/matrix.py:27-41), so a
+ * caller holding such an array passes it as it is.  A point's columns are contiguous there: the scatter
+ * stages them straight from the caller's rows and the permutation into the operator's point order costs
+ * no pass of its own (column-major blocks pay two, lmc_mvm).  ldx, ldy >= P.  lmc_mvm_rows_host copies
+ * the block in, multiplies and copies the result out (no pipelining: every column needs every row).  */
+int lmc_mvm_rows(lmc_op* op, const double* X_dev, long ldx, int P, double* Y_dev, long ldy, void* stream);
+int lmc_mvm_rows_host(lmc_op* op, const double* X_host, long ldx, int P, double* Y_host, long ldy);
 /* unit-testable stages.  Grid vectors are [P][D*m], output-major (likelihood.py:30):
  *   lmc_to_grid    G = W^T V      (WT.dot, ski.py:16)
  *   lmc_grid_mvm   GOUT = (sum_q B_q (x) T_q) GIN   (grid_kernel.py:126-136)

@@ -58,6 +58,8 @@ SIGNATURES = {
     'lmc_mvm': (_i, [_p, _p, _l, _i, _p, _p]),
     'lmc_mvm_host': (_i, [_p, _p, _l, _i, _p]),
     'lmc_mvm_sorted': (_i, [_p, _p, _l, _i, _p, _p]),
+    'lmc_mvm_rows': (_i, [_p, _p, _l, _i, _p, _l, _p]),
+    'lmc_mvm_rows_host': (_i, [_p, _p, _l, _i, _p, _l]),
     'lmc_to_grid': (_i, [_p, _p, _l, _i, _p, _p]),
     'lmc_grid_mvm': (_i, [_p, _p, _i, _p, _p]),
     'lmc_from_grid': (_i, [_p, _p, _i, _p, _l, _p]),

@@ -176,6 +176,40 @@ int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_
     return op_mvm(op, cv, (cudaStream_t)stream);
 }
 
+int lmc_mvm_rows(lmc_op* op, const double* X_dev, long ldx, int P, double* Y_dev, long ldy, void* stream) {
+    LMC_REQUIRE(op, "null argument");
+    if (P == 0) return 0;
+    LMC_REQUIRE(X_dev && Y_dev, "null argument");
+    LMC_REQUIRE(P >= 0 && ldx >= P && ldy >= P, "bad block shape");
+    LMC_REQUIRE(X_dev != Y_dev, "in-place product not supported");
+    return op_mvm_rows(op, X_dev, ldx, P, Y_dev, ldy, (cudaStream_t)stream);
+}
+
+int lmc_mvm_rows_host(lmc_op* op, const double* X_host, long ldx, int P, double* Y_host, long ldy) {
+    LMC_REQUIRE(op, "null argument");
+    if (P == 0) return 0;
+    LMC_REQUIRE(X_host && Y_host, "null argument");
+    LMC_REQUIRE(P >= 0 && ldx >= P && ldy >= P, "bad block shape");
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
+    const long n = op->ps.n;
+    LMC_CHECK(cudaDeviceSynchronize());   // shares the grid workspace with the stream-ordered entry points
+    const size_t need = (size_t)n * P;
+    if (need > op->rows_cap) {
+        cudaFree(op->rows_in); cudaFree(op->rows_out);
+        op->rows_in = op->rows_out = nullptr;
+        op->rows_cap = 0;
+        LMC_CHECK(cudaMalloc(&op->rows_in, sizeof(double) * need));
+        LMC_CHECK(cudaMalloc(&op->rows_out, sizeof(double) * need));
+        op->rows_cap = need;
+    }
+    LMC_CHECK(cudaMemcpy2D(op->rows_in, sizeof(double) * P, X_host, sizeof(double) * ldx, sizeof(double) * P, n,
+                           cudaMemcpyHostToDevice));
+    LMC_TRY(op_mvm_rows(op, op->rows_in, P, P, op->rows_out, P, nullptr));
+    LMC_CHECK(cudaMemcpy2D(Y_host, sizeof(double) * ldy, op->rows_out, sizeof(double) * P, sizeof(double) * P, n,
+                           cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // Host buffers in, host buffers out.  The block is cut into chunks of columns that flow through a
 // 3-stage pipeline (H2D copy | product | D2H copy) on three streams with double-buffered device
 // staging, so PCIe traffic in both directions overlaps the kernels.  With pinned host memory the

@@ -192,6 +192,8 @@ struct InterpArgs {
     int nb0, nb1;
     int tiles, tiles1;
     int extra;             // 2-D strip scatter: the odd last column rides along with the last group of pairs
+    const double* in_rows; // 1-D and 2-D strip scatter: point-major block in[point][column] (row stride ldr), caller's order
+    long ldr;
 };
 
 __device__ __forceinline__ bool group_active(const InterpArgs& a, int c0, int cnt) {
@@ -225,6 +227,25 @@ __device__ __forceinline__ void stage_point_values(double* v, int i, const doubl
     for (int c = ncol; c < 2 * G; ++c) dst[(c & 1) * (CAP * VP) + (c >> 1)] = 0.0;
 }
 
+// Same destination layout from a point-major block (numpy's C order for an [n, P] array): the 2G columns
+// of a staged point are 16 G contiguous bytes of its row, so a group of 2G lanes copies one point with one
+// coalesced request, whatever row of the caller's array the point lives in -- the permutation into sorted
+// order costs nothing extra here (column-major blocks need a pass of their own for it, permute_cols).
+template <int G, int CAP>
+__device__ __forceinline__ void stage_rows(double* v, const int* src, int npts, const double* rows, long ldr,
+                                           int ncol, bool extra, int tid) {
+    constexpr int VP = G + 1, LPP = 2 * G, PPW = 32 / LPP;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int sub = lane / LPP, c = lane % LPP;
+    double* dst0 = v + (c & 1) * (CAP * VP) + (c >> 1);
+    for (int i = warp * PPW + sub; i < npts; i += 8 * PPW) {
+        const double* row = rows + (long)src[i] * ldr;
+        if (c < ncol) cp_async8(dst0 + i * VP, row + c);
+        else dst0[i * VP] = 0.0;
+        if (extra && c == 0) cp_async8(v + i * VP + G, row + 2 * G);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // The scatter kernels (W^T v) are "pair parallel": the lanes of a (part of a)
 // warp are G different RHS pairs working on the SAME grid bins / cells.  That
@@ -250,9 +271,10 @@ template <int G, int CAP>
 struct Scatter1Smem {
     double2 w[CAP][2];            // Keys weights of the 4 taps
     double v[2][CAP * (G + 1)];   // reused for the partial sums
+    int src[CAP];                 // point-major input: the caller's row of every staged point
 };
 
-template <int G, int CAP>
+template <int G, int CAP, bool ROWS>
 __global__ void __launch_bounds__(256, CAP <= 256 ? 4 : 2) to_grid_1d_v3_kernel(const InterpArgs a) {
     typedef Scatter1Smem<G, CAP> Smem;
     constexpr int NBIN = 256 / G, TC = NBIN - 3, VP = G + 1;
@@ -291,7 +313,12 @@ __global__ void __launch_bounds__(256, CAP <= 256 ? 4 : 2) to_grid_1d_v3_kernel(
             s.w[i][0] = make_double2(w[0], w[1]);
             s.w[i][1] = make_double2(w[2], w[3]);
             const long src = a.perm_in ? (long)a.perm_in[gi] : (long)gi;
-            stage_point_values<G, CAP>(s.v[0], i, a.in + (long)col0 * a.ld + src, a.ld, ncol);
+            if (ROWS) s.src[i] = (int)src;
+            else stage_point_values<G, CAP>(s.v[0], i, a.in + (long)col0 * a.ld + src, a.ld, ncol);
+        }
+        if (ROWS) {
+            __syncthreads();
+            stage_rows<G, CAP>(s.v[0], s.src, cnt, a.in_rows + col0, a.ldr, ncol, false, tid);
         }
         cp_async_commit();
         cp_async_wait_all();
@@ -515,7 +542,7 @@ struct Tile3Smem {
     int live[64];                 // per group of this CTA: any column still active
 };
 
-template <int G, int TX, int TY, int CAP>
+template <int G, int TX, int TY, int CAP, bool ROWS>
 __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs a, int groups_per_cta) {
     typedef Tile3Smem<G, TX, TY, CAP> Smem;
     static_assert((TX / 4) * TY * G == 256, "one thread per (strip, pair)");
@@ -586,7 +613,7 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
     __syncthreads();
 
     const int i_a = tid, i_b = tid + 256;   // the (up to) two staged points this thread copies
-    const long src_a = i_a < npts ? s.src[i_a] : 0, src_b = i_b < npts ? s.src[i_b] : 0;
+    const long src_a = (!ROWS && i_a < npts) ? s.src[i_a] : 0, src_b = (!ROWS && i_b < npts) ? s.src[i_b] : 0;
     const int g = tid & (G - 1);
     const int strip = tid / G;
     const int sy = strip % TY, sx = strip / TY;
@@ -603,9 +630,13 @@ __global__ void __launch_bounds__(256, 2) to_grid_2d_v3_kernel(const InterpArgs 
         const bool extra = a.extra && grp == ngroups - 1;    // uniform over the CTA
         if (live) {
             const int ncol = min(2 * G + (extra ? 1 : 0), a.ncols - col0);
-            const double* gp = a.in + (long)col0 * a.ld;
-            if (i_a < npts) stage_point_values<G, CAP>(s.v[0], i_a, gp + src_a, a.ld, ncol);
-            if (i_b < npts) stage_point_values<G, CAP>(s.v[0], i_b, gp + src_b, a.ld, ncol);
+            if (ROWS) {
+                stage_rows<G, CAP>(s.v[0], s.src, npts, a.in_rows + col0, a.ldr, min(ncol, 2 * G), extra, tid);
+            } else {
+                const double* gp = a.in + (long)col0 * a.ld;
+                if (i_a < npts) stage_point_values<G, CAP>(s.v[0], i_a, gp + src_a, a.ld, ncol);
+                if (i_b < npts) stage_point_values<G, CAP>(s.v[0], i_b, gp + src_b, a.ld, ncol);
+            }
             cp_async_commit();
             cp_async_wait_all();
         }
@@ -1006,6 +1037,137 @@ int permute_cols(const PointSet& ps, bool to_sorted, const double* in, long ld, 
     return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------------------
+// Point-major blocks (rows[i][c], numpy's C order for an [n, P] array, caller's point order) <-> the
+// operator's sorted column-major layout.  A CTA owns 32 consecutive sorted points and up to kRowChunk
+// columns: whole row pieces on the point-major side, 256-byte column pieces on the other, transposed
+// through shared memory -- both sides move full sectors, unlike a permutation of column-major data
+// (one 32-byte sector per 8-byte element).
+// ---------------------------------------------------------------------------
+static const int kRowChunk = 136, kRowPitch = kRowChunk + 1;
+
+// cols[c][j] = rows[perm[j]][c]
+__global__ void __launch_bounds__(256) rows_to_sorted_cols_kernel(const double* __restrict__ rows, long ldr,
+                                                                  const int* __restrict__ perm, long n, int ncols,
+                                                                  double* __restrict__ cols, long ldc) {
+    __shared__ double tile[32 * kRowPitch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long j0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * kRowChunk;
+    const int cw = min(kRowChunk, ncols - c0);
+    for (int p = warp; p < 32; p += 8) {
+        const long j = j0 + p;
+        if (j >= n) break;
+        const double* row = rows + (long)(perm ? perm[j] : j) * ldr + c0;
+        for (int c = lane; c < cw; c += 32) tile[p * kRowPitch + c] = __ldcs(row + c);
+    }
+    __syncthreads();
+    if (j0 + lane < n)
+        for (int c = warp; c < cw; c += 8) cols[(long)(c0 + c) * ldc + j0 + lane] = tile[lane * kRowPitch + c];
+}
+
+// rows_out[perm[j]][c] = cols[c][j] + noise[d(j)] * rows_in[perm[j]][c]   (the D v term of K~ v, same
+// fused multiply-add as the gather kernels' epilogue).  All loads of a phase are issued before their first
+// use: the pass is pure data movement (3 x 8 n P bytes) and lives off the bytes it keeps in flight.
+__global__ void __launch_bounds__(256, 4) sorted_cols_to_rows_kernel(const double* __restrict__ cols, long ldc,
+                                                                  const int* __restrict__ perm, long n, int ncols,
+                                                                  const double* __restrict__ noise,
+                                                                  const long* __restrict__ out_start, int D,
+                                                                  const double* __restrict__ rows_in, long ldi,
+                                                                  double* __restrict__ rows_out, long ldo) {
+    __shared__ double tile[32 * kRowPitch];
+    constexpr int CI = (kRowChunk + 31) / 32;    // columns per lane on the row side
+    constexpr int CJ = (kRowChunk + 7) / 8;      // columns per warp on the column side
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long j0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * kRowChunk;
+    const int cw = min(kRowChunk, ncols - c0);
+    // this warp's 4 points: row index and noise, one lane each, handed round by shuffle
+    long my_row = 0;
+    double my_nz = 0.0;
+    {
+        const long j = j0 + 4 * warp + (lane & 3);
+        if (j < n) {
+            my_row = perm ? perm[j] : j;
+            if (noise) {
+                int d = 0;
+                while (d + 1 < D && j >= out_start[d + 1]) ++d;
+                my_nz = noise[d];
+            }
+        }
+    }
+    {
+        double v[CJ];
+        const bool have = j0 + lane < n;
+#pragma unroll
+        for (int k = 0; k < CJ; ++k) {
+            const int c = warp + 8 * k;
+            v[k] = (have && c < cw) ? __ldcs(cols + (long)(c0 + c) * ldc + j0 + lane) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < CJ; ++k) {
+            const int c = warp + 8 * k;
+            if (c < cw) tile[lane * kRowPitch + c] = v[k];
+        }
+    }
+    // the input rows of the noise term: in flight across the barrier
+    double x[4][CI];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const long r = __shfl_sync(0xffffffffu, my_row, p);
+#pragma unroll
+        for (int k = 0; k < CI; ++k) {
+            const int c = lane + 32 * k;
+            x[p][k] = (noise && c < cw && j0 + 4 * warp + p < n) ? __ldcs(rows_in + r * ldi + c0 + c) : 0.0;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const long r = __shfl_sync(0xffffffffu, my_row, p);
+        const double nz = __shfl_sync(0xffffffffu, my_nz, p);
+        if (j0 + 4 * warp + p >= n) continue;
+        double* yout = rows_out + r * ldo + c0;
+#pragma unroll
+        for (int k = 0; k < CI; ++k) {
+            const int c = lane + 32 * k;
+            if (c < cw) {
+                double v = tile[(4 * warp + p) * kRowPitch + c];
+                if (noise) v = fma(nz, x[p][k], v);
+                __stcs(yout + c, v);
+            }
+        }
+    }
+}
+
+int rows_to_sorted_cols(const PointSet& ps, const double* rows, long ldr, int ncols, double* cols, long ldc,
+                        cudaStream_t st) {
+    if (ncols == 0) return 0;
+    ProfScope prof(PROF_OTHER, st);
+    const dim3 grid((unsigned)ceil_div(ps.n, 32), (unsigned)ceil_div(ncols, kRowChunk));
+    rows_to_sorted_cols_kernel<<<grid, 256, 0, st>>>(rows, ldr, ps.identity ? nullptr : ps.perm, ps.n, ncols, cols, ldc);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int sorted_cols_to_rows(const PointSet& ps, const double* cols, long ldc, int ncols, const double* noise,
+                        const double* rows_in, long ldi, double* rows_out, long ldo, cudaStream_t st) {
+    if (ncols == 0) return 0;
+    ProfScope prof(PROF_OTHER, st);
+    const dim3 grid((unsigned)ceil_div(ps.n, 32), (unsigned)ceil_div(ncols, kRowChunk));
+    sorted_cols_to_rows_kernel<<<grid, 256, 0, st>>>(cols, ldc, ps.identity ? nullptr : ps.perm, ps.n, ncols, noise,
+                                                     ps.out_start_dev, ps.D, rows_in, ldi, rows_out, ldo);
+    count_launch();
+    LMC_CHECK(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -1018,6 +1180,7 @@ static InterpArgs make_args(const PointSet& ps, const ColumnView& cv) {
     a.bin_start = ps.bin_start;
     a.out_start = ps.out_start_dev;
     a.in = cv.in; a.out = cv.out; a.ld = cv.ld; a.ldo = cv.ld_out ? cv.ld_out : cv.ld;
+    if (cv.rows_in) { a.in_rows = cv.in; a.ldr = cv.ld; a.in = nullptr; }
     a.ncols = cv.ncols;
     a.in_scale = cv.in_scale; a.active = cv.active;
     a.grid_pitch = ps.grid_pitch;
@@ -1032,10 +1195,7 @@ static int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
+static const int kCap16 = 304, kCap8 = 448;   // staged points per CTA: 8x8 tile (16 pair lanes), 16x8 tile (8 lanes)
 
 // which 2-D scatter kernel a segment of RHS pairs goes through
 enum ScatterKind { SCATTER_AUTO, SCATTER_G16, SCATTER_G8, SCATTER_PAIR, SCATTER_G16X, SCATTER_G8X };
@@ -1046,7 +1206,11 @@ template <int G, int TX, int TY, int CAP>
 static int launch_strips(const PointSet& ps, InterpArgs a, int npairs, cudaStream_t st) {
     typedef Tile3Smem<G, TX, TY, CAP> Smem;
     static bool attr3 = false;
-    if (!attr3) { LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP>, sizeof(Smem))); attr3 = true; }
+    if (!attr3) {
+        LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP, false>, sizeof(Smem)));
+        LMC_TRY(set_smem(to_grid_2d_v3_kernel<G, TX, TY, CAP, true>, sizeof(Smem)));
+        attr3 = true;
+    }
     a.tiles1 = ceil_div(ps.m[1], TY);
     a.tiles = ceil_div(ps.m[0], TX) * a.tiles1;
     if (a.extra) npairs -= 1;                     // the odd last column rides with the last full group
@@ -1056,31 +1220,27 @@ static int launch_strips(const PointSet& ps, InterpArgs a, int npairs, cudaStrea
     int gpc = std::min(ngroups, 64);
     while (gpc > 1 && ctas1 * ceil_div(ngroups, gpc) < 148L * 2 * 4) gpc = (gpc + 1) / 2;
     dim3 grid3((unsigned)ctas1, (unsigned)ceil_div(ngroups, gpc));
-    to_grid_2d_v3_kernel<G, TX, TY, CAP><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
+    if (a.in_rows) to_grid_2d_v3_kernel<G, TX, TY, CAP, true><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
+    else to_grid_2d_v3_kernel<G, TX, TY, CAP, false><<<grid3, 256, sizeof(Smem), st>>>(a, gpc);
     return 0;
 }
 
-static const int kCap16 = 304, kCap8 = 448;   // staged points per CTA: 8x8 tile (16 pair lanes), 16x8 tile (8 lanes)
+struct ScatterSeg { int first, count; ScatterKind kind; };
 
-int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) {
-    if (cv.ncols == 0) return 0;
-    ProfScope prof(PROF_TO_GRID, st);
-    const int npairs = (cv.ncols + 1) / 2;
+// 2-D: the strip kernel's lanes are RHS pairs, 16 per group.  A block whose pair count is not a
+// multiple of 16 (y plus an even number of probes; the 8 or 9 pairs a rank holds when 128 probes
+// are sharded over 8 GPUs) would idle the lanes of its last group, so the remainder is split off:
+// up to 8 pairs go through the 8-lane variant (16x8-cell tiles), one or two left-over pairs through
+// the one-pair-per-CTA kernel.  Returns the number of segments, 0 when the strip kernels do not apply.
+static int scatter_plan(const PointSet& ps, int ncols, ScatterSeg (&segs)[3]) {
     static const int variant = env_int("LMC_TOGRID2D", 3);
-    if (ps.ndim != 2 || variant < 3 || ps.max_tile_pts_8x8 > kCap16)
-        return to_grid_launch(ps, cv, G, SCATTER_AUTO, st);
-    // 2-D: the strip kernel's lanes are RHS pairs, 16 per group.  A block whose pair count is not a
-    // multiple of 16 (y plus an even number of probes; the 8 or 9 pairs a rank holds when 128 probes
-    // are sharded over 8 GPUs) would idle the lanes of its last group, so the remainder is split off:
-    // up to 8 pairs go through the 8-lane variant (16x8-cell tiles), one or two left-over pairs through
-    // the one-pair-per-CTA kernel.
+    if (ps.ndim != 2 || variant < 3 || ps.max_tile_pts_8x8 > kCap16) return 0;
+    const int npairs = (ncols + 1) / 2;
     const bool g8_ok = ps.max_tile_pts_16x8 <= kCap8;
-    struct Seg { int first, count; ScatterKind kind; };
-    Seg segs[3];
     int nseg = 0;
     int done = npairs / 16 * 16, rem = npairs - done;
     static const bool no_extra = getenv("LMC_NO_EXTRACOL") != nullptr;
-    if ((cv.ncols & 1) && !no_extra && (rem == 1 || (rem == 9 && g8_ok)) && npairs > 1) {
+    if ((ncols & 1) && !no_extra && (rem == 1 || (rem == 9 && g8_ok)) && npairs > 1) {
         // 16 k (+ 8) pairs and one odd column: the column rides along as a third accumulator of the last
         // group (129 columns on one GPU, the 17 of a rank when 128 probes are sharded over 8)
         if (rem == 1) {
@@ -1101,11 +1261,32 @@ int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) 
     }
     if (rem >= 1 && rem <= 2 && done > 0) segs[nseg++] = {done, rem, SCATTER_PAIR};
     else if (rem) segs[nseg++] = {done, rem, SCATTER_G16};
+    return nseg;
+}
+
+bool to_grid_takes_rows(const PointSet& ps, int ncols) {
+    static const bool off = getenv("LMC_NO_ROWS_SCATTER") != nullptr;
+    if (off || ps.identity) return false;
+    if (ps.ndim == 1) return true;
+    ScatterSeg segs[3];
+    const int nseg = scatter_plan(ps, ncols, segs);
+    for (int i = 0; i < nseg; ++i)
+        if (segs[i].kind == SCATTER_PAIR) return false;
+    return nseg > 0;
+}
+
+int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st) {
+    if (cv.ncols == 0) return 0;
+    ProfScope prof(PROF_TO_GRID, st);
+    ScatterSeg segs[3];
+    const int nseg = scatter_plan(ps, cv.ncols, segs);
+    if (cv.rows_in) LMC_REQUIRE(to_grid_takes_rows(ps, cv.ncols), "point-major block not supported by this scatter");
+    if (nseg == 0) return to_grid_launch(ps, cv, G, SCATTER_AUTO, st);
     for (int i = 0; i < nseg; ++i) {
         ColumnView part = cv;
         const int c0 = 2 * segs[i].first;
         part.ncols = std::min(2 * segs[i].count, cv.ncols - c0);
-        part.in = cv.in + (long)c0 * cv.ld;
+        part.in = cv.rows_in ? cv.in + c0 : cv.in + (long)c0 * cv.ld;
         part.in_scale = cv.in_scale ? cv.in_scale + c0 : nullptr;
         part.active = cv.active ? cv.active + c0 : nullptr;
         LMC_TRY(to_grid_launch(ps, part, G + (size_t)segs[i].first * ps.D * ps.grid_pitch, segs[i].kind, st));
@@ -1124,15 +1305,22 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
         static bool attr = false;
         static const int cap_sel = env_int("LMC_TG1_CAP", CAP1S);   // 256: four CTAs per SM (0.125 -> 0.101 ms at config D)
         if (!attr) {
-            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1>, sizeof(Smem)));
-            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1S>, sizeof(SmemS)));
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1, false>, sizeof(Smem)));
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1S, false>, sizeof(SmemS)));
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1, true>, sizeof(Smem)));
+            LMC_TRY(set_smem(to_grid_1d_v3_kernel<G1, CAP1S, true>, sizeof(SmemS)));
             attr = true;
         }
         const int TC = 256 / G1 - 3;
         a.tiles = ceil_div(ps.m[0], TC);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
-        if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S><<<grid, 256, sizeof(SmemS), st>>>(a);
-        else to_grid_1d_v3_kernel<G1, CAP1><<<grid, 256, sizeof(Smem), st>>>(a);
+        if (a.in_rows) {
+            if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S, true><<<grid, 256, sizeof(SmemS), st>>>(a);
+            else to_grid_1d_v3_kernel<G1, CAP1, true><<<grid, 256, sizeof(Smem), st>>>(a);
+        } else {
+            if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S, false><<<grid, 256, sizeof(SmemS), st>>>(a);
+            else to_grid_1d_v3_kernel<G1, CAP1, false><<<grid, 256, sizeof(Smem), st>>>(a);
+        }
     } else if (kind == SCATTER_G16 || kind == SCATTER_G16X) {
         a.extra = kind == SCATTER_G16X;
         LMC_TRY((launch_strips<16, 8, 8, kCap16>(ps, a, npairs, st)));

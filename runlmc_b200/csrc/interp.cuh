@@ -49,12 +49,20 @@ struct ColumnView {
     const int* active = nullptr;       // optional per-column flag; pairs with no active column are skipped
     bool sorted_in = false;            // `in` already is in the operator's sorted point order
     bool sorted_out = false;           // `out` is wanted in sorted order
+    bool rows_in = false;              // `in` is point-major: in[point][column], row stride ld, caller's order
+                                       // (to_grid only, where to_grid_takes_rows() says so)
 };
 
 // block of columns between the caller's point order and the sorted order (out[c][i] = in[c][p[i]],
 // p = perm when to_sorted, else its inverse)
 int permute_cols(const PointSet& ps, bool to_sorted, const double* in, long ld, int ncols, double* out,
                  long ldo, cudaStream_t st);
+// point-major blocks (rows[i][c], caller's order) <-> sorted column-major; the way back adds noise_d * rows_in
+int rows_to_sorted_cols(const PointSet& ps, const double* rows, long ldr, int ncols, double* cols, long ldc,
+                        cudaStream_t st);
+int sorted_cols_to_rows(const PointSet& ps, const double* cols, long ldc, int ncols, const double* noise,
+                        const double* rows_in, long ldi, double* rows_out, long ldo, cudaStream_t st);
+bool to_grid_takes_rows(const PointSet& ps, int ncols);
 // G[pair][d][cell] (complex pairs of columns 2p, 2p+1)  <-  W^T in     (deterministic, no atomics)
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st);
 // out = W G (+ noise_d * in when noise != nullptr)

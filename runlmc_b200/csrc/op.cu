@@ -132,6 +132,41 @@ int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st) {
     return 0;
 }
 
+// K~ applied to a point-major block: X[i][c], Y[i][c] (numpy's C order for the [n, P] argument of the
+// reference's Matrix.matmat, linalg/matrix.py:27-41), points in the caller's order.  The scatter stages its
+// points straight from the rows of X (a point's columns are contiguous there, so the permutation into
+// sorted order costs no pass of its own), the gather leaves its result in sorted column-major scratch and
+// one transposing pass writes the rows of Y, adding the noise term D v on the way.
+int op_mvm_rows(lmc_op* op, const double* X, long ldx, int P, double* Y, long ldy, cudaStream_t st) {
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
+    if (P == 0) return 0;
+    LMC_TRY(op_ensure_workspace(op));
+    const int npairs = (P + 1) / 2;
+    const long n = op->ps.n;
+    if (!op->Vs) LMC_CHECK(cudaMalloc(&op->Vs, sizeof(double) * (size_t)2 * op->g_pairs * n));
+    const int nblocks = ceil_div(npairs, op->g_pairs);
+    const int per_block = ceil_div(npairs, nblocks);
+    for (int p0 = 0; p0 < npairs; p0 += per_block) {
+        const int cnt = std::min(per_block, npairs - p0);
+        const int c0 = 2 * p0;
+        ColumnView t;
+        t.ncols = std::min(2 * cnt, P - c0);
+        if (to_grid_takes_rows(op->ps, t.ncols)) {
+            t.in = X + c0; t.ld = ldx; t.rows_in = true;
+        } else {
+            LMC_TRY(rows_to_sorted_cols(op->ps, X + c0, ldx, t.ncols, op->Vs, n, st));
+            t.in = op->Vs; t.ld = n; t.sorted_in = true;
+        }
+        LMC_TRY(to_grid(op->ps, t, op->G, st));
+        LMC_TRY(op_grid_block(op, op->G, cnt, st));
+        ColumnView u;
+        u.out = op->Vs; u.ld = u.ld_out = n; u.ncols = t.ncols; u.sorted_in = u.sorted_out = true;
+        LMC_TRY(from_grid(op->ps, u, op->G, nullptr, st));
+        LMC_TRY(sorted_cols_to_rows(op->ps, op->Vs, n, t.ncols, op->noise, X + c0, ldx, Y + c0, ldy, st));
+    }
+    return 0;
+}
+
 }  // namespace lmc
 
 lmc_op::~lmc_op() {
@@ -145,6 +180,8 @@ lmc_op::~lmc_op() {
     }
     for (int i = 0; i < 3; ++i)
         if (hs[i]) cudaStreamDestroy(hs[i]);
+    cudaFree(rows_in);
+    cudaFree(rows_out);
     cudaFree(spec);
     cudaFree(specL);
     cudaFree(specP);

@@ -55,6 +55,9 @@ struct lmc_op {
     double* stage_in[2] = {nullptr, nullptr};
     double* stage_out[2] = {nullptr, nullptr};
     size_t stage_cap = 0;   // doubles per staging buffer
+    double* rows_in = nullptr;   // device copies of a point-major host block (lmc_mvm_rows_host)
+    double* rows_out = nullptr;
+    size_t rows_cap = 0;
     // block-solver state vectors (MINRES: 8 [P][n] blocks, CG: 5), grow-only, kept between solves:
     // cudaMalloc/cudaFree of ~8 n P doubles per solve would cost as much as tens of iterations
     void* solver_ws = nullptr;
@@ -86,6 +89,7 @@ namespace lmc {
 int op_ensure_workspace(lmc_op* op);
 // OUT = K~ V for ncols columns described by cv (cv.in / cv.out), noise included
 int op_mvm(lmc_op* op, const ColumnView& cv, cudaStream_t st);
+int op_mvm_rows(lmc_op* op, const double* X, long ldx, int P, double* Y, long ldy, cudaStream_t st);
 // same without the noise term and with explicit spectra / mixing matrices
 // (used by the gradient stage); spec/B device pointers, Q kernels
 int op_grid_block(lmc_op* op, cplx* G, int cnt, cudaStream_t st);

@@ -209,7 +209,29 @@ class FusedLMC:
         return self.mvm(np.asarray(x, dtype=np.float64).reshape(-1))
 
     def matmat(self, X):
-        return self.mvm(np.asarray(X, dtype=np.float64).T).T
+        """K~ X for an [n, P] array, the reference's Matrix.matmat (linalg/matrix.py:27-41).  A C-ordered
+        array goes to the device as it is (point-major entry point, no host transposition); a
+        Fortran-ordered one is P contiguous columns and takes the pipelined column path."""
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim != 2 or X.shape[0] != self.n:
+            raise ValueError('expected block of shape ({}, P), got {}'.format(self.n, X.shape))
+        if X.flags['F_CONTIGUOUS'] and not X.flags['C_CONTIGUOUS']:
+            return self.mvm(X.T).T
+        X = np.ascontiguousarray(X)
+        out = np.empty_like(X)
+        P = X.shape[1]
+        nat.check(nat.lib.lmc_mvm_rows_host(self._h, nat.host_ptr(X), P, P, nat.host_ptr(out), P))
+        return out
+
+    def matmat_device(self, X, out=None):
+        """X: torch float64 CUDA tensor [n, P], contiguous (point-major).  Stream ordered."""
+        torch = nat.require_cuda()
+        assert X.is_cuda and X.dtype == torch.float64 and X.is_contiguous() and X.shape[0] == self.n
+        if out is None:
+            out = torch.empty_like(X)
+        P = X.shape[1]
+        nat.check(nat.lib.lmc_mvm_rows(self._h, _dev(X), P, P, _dev(out), P, nat.current_stream_ptr()))
+        return out
 
     def mvm_device(self, V, out=None):
         """V: torch float64 CUDA tensor [P, n] (row stride = n). Stream ordered."""

@@ -98,6 +98,26 @@ def test_stages_and_mvm(name):
     assert rel_err(out, want[:, perm]) < MVM_TOL
 
 
+@pytest.mark.parametrize('name', sorted(PROBLEMS))
+@pytest.mark.parametrize('P', [1, 4, 7])
+def test_point_major_blocks(name, P):
+    """lmc_mvm_rows (X[i][c], the reference's matmat argument as numpy lays it out) against the oracle and,
+    bit for bit, against the column-major entry point -- on every geometry, i.e. through the direct row
+    staging of the 2-D strip scatter and through the transposing fallback of all other scatters."""
+    import torch
+    prob = PROBLEMS[name]()
+    op = fused_from_problem(prob)
+    _, ref = oracle_from_problem(prob)
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((prob.n, P))
+    Xd = torch.as_tensor(X, device='cuda')
+    Y = op.matmat_device(Xd).cpu().numpy()
+    for c in range(P):
+        assert rel_err(Y[:, c], ref.matvec(X[:, c])) < MVM_TOL
+    assert np.array_equal(Y, op.mvm_device(Xd.t().contiguous()).cpu().numpy().T)
+    assert np.array_equal(op.matmat(X), Y)
+
+
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
 def test_mvm_against_reference_golden(name):
     from test_oracle_golden import GOLDEN_PROBLEMS
@@ -175,8 +195,16 @@ def test_wide_blocks_match_narrow_blocks_and_oracle(ndim):
         Vs = torch.as_tensor(np.ascontiguousarray(V[:P][:, perm]), device='cuda')
         wide_sorted = op.mvm_sorted_device(Vs).cpu().numpy()
         assert max(rel_err(wide_sorted[c], narrow[c][perm]) for c in range(P)) < 1e-12
-    # host-buffer entry point on a wide block
+        # point-major block ([n, P], numpy's C order): same staged values, same summation order
+        rows = op.matmat_device(Vd[:P].t().contiguous()).cpu().numpy()
+        assert np.array_equal(rows, wide.T)
+    # host-buffer entry points on a wide block
     assert rel_err(op.mvm(V[:67]), narrow[:67]) < 1e-12
+    X = np.ascontiguousarray(V[:67].T)
+    assert rel_err(op.matmat(X), op.mvm(V[:67]).T) < 1e-12     # the column path cuts the block into chunks
+    assert np.array_equal(op.matmat(X), op.matmat_device(torch.as_tensor(X, device='cuda')).cpu().numpy())
+    assert rel_err(op.matmat(np.asfortranarray(X)), op.matmat(X)) < 1e-12
+    assert rel_err(op.matmat(X[:, :5]), op.matmat(X)[:, :5]) < 1e-12     # a strided view is copied first
 
 
 @pytest.mark.parametrize('P', [35, 33])

@@ -52,7 +52,10 @@ def main():
     V = torch.randn(P, prob.n, dtype=torch.float64, device='cuda')
     out = torch.empty_like(V)
     alg = 16.0 * prob.n * P + 8.0 * prob.ndim * prob.n
+    VR = V.t().contiguous()
+    outR = torch.empty_like(VR)
     for label, fn in (('caller order', lambda: op.mvm_device(V, out)),
+                      ('caller order, point-major', lambda: op.matmat_device(VR, outR)),
                       ('sorted order', lambda: op.mvm_sorted_device(V, out))):
         ms, prof = timed(fn, args.iters)
         print('%s %s P=%d: %.3f ms/step  %.0f MVM*RHS/s  alg %.0f GB/s' % (
