@@ -144,6 +144,17 @@ class FusedSumMatrix(SumMatrix):
             return super()._apply_dev(X)
         return fused.mvm_device(X.contiguous())
 
+    def matmat(self, X):
+        """[n, P] block as the caller holds it: a C-ordered array goes through the point-major entry point
+        (lmc_mvm_rows_host), without the two host transpositions of the generic Matrix.matmat."""
+        fused = self._fused
+        if fused is None:
+            return super().matmat(X)
+        X = np.asarray(X)
+        if X.ndim != 2 or X.shape[0] != self.shape[1]:
+            raise ValueError('dimension mismatch: {} vs {}'.format(X.shape, self.shape))
+        return fused.matmat(X)
+
     def __getstate__(self):
         state = super().__getstate__()
         state['_handle'] = None      # device handles are not picklable

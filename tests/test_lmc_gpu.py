@@ -45,6 +45,7 @@ def test_gen_grid_kernel_matvec(name, fuse):
     for v, kv in zip(g['V'], g['KV']):
         assert rel_err(K.matvec(v), kv) < 1e-10
     assert rel_err(K.matmat(g['V'].T), g['KV'].T) < 1e-10
+    assert rel_err(K.matmat(np.ascontiguousarray(g['V'].T)), g['KV'].T) < 1e-10     # C order: point-major path
     if not fuse:
         for rep in ('sum', 'bt', 'slfm'):
             if 'KV_' + rep in g:
