@@ -168,6 +168,19 @@ int lmc_minres_generic_pre(int (*apply_cb)(void*), int (*precond_cb)(void*), voi
                            int P, double* X_dev, double tol, int maxiter, int check_every, int* iters_host,
                            double* resid_host, int* istop_host, void* stream);
 
+/* ---- log-determinant by-product ------------------------------------------------
+ * The reference's roadmap (README.md:88-93, "Lanczos") and its model's log_det_K (models/
+ * interpolated_llgp.py:262-276, a dense Cholesky) ask for a matrix-free log det K~.  MINRES is a Lanczos
+ * process: lmc_minres_lanczos is lmc_minres that also hands back the tridiagonal of every column,
+ * tridiag_host[c][j] = (alfa_{j+1}, beta_{j+2}) for the first min(k, iterations of c) iterations (zero
+ * beyond), and beta1_host[c] = ||b_c||.  With Rademacher right-hand sides z_c,
+ *   z_c^T log(K~) z_c ~= beta1_c^2 * e1^T log(T_c) e1
+ * (stochastic Lanczos quadrature), so the probe solves of one gradient evaluation also estimate
+ * log det K~ = E[z^T log(K~) z] at no extra product (runlmc_b200/approx/logdet.py).               */
+int lmc_minres_lanczos(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol,
+                       int maxiter, int check_every, int* iters_host, double* resid_host, int* istop_host,
+                       int k, double* tridiag_host, double* beta1_host, void* stream);
+
 /* ---- batched conjugate gradients ---------------------------------------------
  * Iterative.solve(..., minres=False) (iterative.py:44-51): scipy.sparse.linalg.cg with M = I, x0 = 0,
  * rtol = min(1e-10, tol), atol = 0, maxiter, behind the same true-residual test every `check_every`-th

@@ -497,8 +497,11 @@ def build_operator(spec, Xs, grids, rep='auto', slfm_identity=(False, False)):
 # reference wrapper runlmc/approx/iterative.py:24-62
 # ---------------------------------------------------------------------------
 
-def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None):
+def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None, record=None):
     """Paige-Saunders MINRES, arithmetic order as scipy's.
+
+    ``record``: optional list; receives (alfa_k, beta_{k+1}) of every iteration, i.e. the Lanczos
+    tridiagonal scipy's recurrence builds (minres.py:247-262), preceded by beta1 as record[0].
 
     ``psolve``: the preconditioner M (an SPD approximation of the INVERSE, scipy's ``M``:
     ``y = psolve(r)``, minres.py:256 and :313), None = identity.  istop = 9 stands for scipy's
@@ -518,6 +521,8 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None):
     if beta1 == 0:
         return x, 0, 0, trace
     beta1 = math.sqrt(beta1)
+    if record is not None:
+        record.append(beta1)
     oldb = 0.0
     beta = beta1
     dbar = 0.0
@@ -553,6 +558,8 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None):
         if beta < 0:
             return x, 9, itn, trace
         beta = math.sqrt(beta)
+        if record is not None:
+            record.append((alfa, beta))
         tnorm2 += alfa ** 2 + oldb ** 2 + beta ** 2
         if itn == 1 and beta / beta1 <= 10 * EPS:
             istop = -1
@@ -607,6 +614,31 @@ def minres(matvec, b, rtol, maxiter, callback=None, trace_at=(), psolve=None):
         if istop != 0:
             break
     return x, istop, itn, trace
+
+
+def lanczos_quadrature_logdet(beta1, coeffs):
+    """z^T log(A) z ~= beta1^2 e1^T log(T_k) e1 for the Lanczos tridiagonal T_k started at z / ||z||
+    (stochastic Lanczos quadrature, Ubaru-Chen-Saad 2017, the "Lanczos" item of the reference's roadmap,
+    README.md:88-93).  ``coeffs``: [(alfa_j, beta_{j+1})] as recorded by ``minres``."""
+    import scipy.linalg
+    k = len(coeffs)
+    if k == 0:
+        return 0.0
+    d = np.array([c[0] for c in coeffs])
+    e = np.array([c[1] for c in coeffs[:-1]])
+    theta, vecs = scipy.linalg.eigh_tridiagonal(d, e)
+    return float(beta1 ** 2 * np.sum(vecs[0] ** 2 * np.log(theta)))
+
+
+def stochastic_logdet(matvec, probes, rtol, maxiter):
+    """log det A ~= mean_i z_i^T log(A) z_i over Rademacher probes, each term from the Lanczos process
+    of the MINRES solve A x = z_i.  Returns (estimate, per-probe terms)."""
+    terms = []
+    for z in probes:
+        rec = []
+        minres(matvec, z, rtol, maxiter, record=rec)
+        terms.append(lanczos_quadrature_logdet(rec[0], rec[1:]))
+    return float(np.mean(terms)), np.array(terms)
 
 
 def cg(matvec, b, rtol, maxiter, callback=None):

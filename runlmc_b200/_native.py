@@ -67,6 +67,7 @@ SIGNATURES = {
     'lmc_minres_host': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p]),
     'lmc_minres_generic': (_i, [_p, _p, _l, _p, _p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
     'lmc_minres_pre': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _i, _p, _p, _p, _p]),
+    'lmc_minres_lanczos': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _i, _p, _p, _p]),
     'lmc_op_diagonal': (_i, [_p, _p]),
     'lmc_minres_generic_pre': (_i, [_p, _p, _p, _l, _p, _p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),
     'lmc_cg': (_i, [_p, _p, _l, _i, _p, _d, _i, _i, _p, _p, _p, _p]),

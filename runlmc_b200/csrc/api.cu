@@ -340,6 +340,14 @@ int lmc_minres(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev,
                         istop_host, (cudaStream_t)stream);
 }
 
+int lmc_minres_lanczos(lmc_op* op, const double* RHS_dev, long ld, int P, double* X_dev, double tol,
+                       int maxiter, int check_every, int* iters_host, double* resid_host, int* istop_host,
+                       int k, double* tridiag_host, double* beta1_host, void* stream) {
+    LMC_REQUIRE(op && RHS_dev && X_dev && tridiag_host, "null argument");
+    return minres_solve_lanczos(op, RHS_dev, ld, P, X_dev, tol, maxiter, check_every, iters_host, resid_host,
+                                istop_host, k, tridiag_host, beta1_host, (cudaStream_t)stream);
+}
+
 // 1 / diag(K~) of the current parameters in sorted order, computed on first use after a parameter update
 static int ensure_jacobi(lmc_op* op, cudaStream_t st) {
     if (op->jacobi_valid) return 0;

@@ -163,7 +163,7 @@ static const int kScalarThreads = 64;   // threads per column in the scalar kern
 // scalar recurrences after the Lanczos step (minres.py:236-283); one block per column so the sum of
 // the per-CTA partials is a parallel reduction (a single thread walking ~500 partials cost 40 us)
 __global__ void minres_s1_kernel(ColState* st, const int* active, const double* part_b, int nblk, int P,
-                                 int* n_active) {
+                                 int* n_active, double* rec, int rec_k) {
     const int col = blockIdx.x;
     if (col == 0 && threadIdx.x == 0) *n_active = 0;   // recounted by the s2 kernel that follows
     if (!active[col]) return;
@@ -176,6 +176,12 @@ __global__ void minres_s1_kernel(ColState* st, const int* active, const double* 
     if (s < 0.0) { c.istop = 9; s_pos = 0.0; }   // r2 . M r2 < 0: scipy raises (indefinite preconditioner)
     c.beta = sqrt(s_pos);
     c.tnorm2 += c.alfa * c.alfa + c.oldb * c.oldb + c.beta * c.beta;
+    if (rec && c.itn <= rec_k) {
+        // the Lanczos tridiagonal of this column: T[k][k] = alfa_k, T[k][k+1] = beta_{k+1} (k = itn)
+        double* r = rec + ((long)col * rec_k + (c.itn - 1)) * 2;
+        r[0] = c.alfa;
+        r[1] = c.beta;
+    }
     if (c.itn == 1 && c.beta / c.beta1 <= 10 * DBL_EPSILON) c.istop = -1;
     c.oldeps = c.epsln;
     c.delta = c.cs * c.dbar + c.sn * c.alfa;
@@ -505,6 +511,7 @@ struct MinresState {
     double *pa, *pb, *pc;
     ColState* cs; double* inv_beta; int* active; int* n_active;
     double rtol; int maxiter;
+    double* rec; int rec_k;                       // optional record of the Lanczos coefficients, [P][rec_k][2]
 };
 
 static int minres_iteration(MinresOperator& A, Preconditioner* M, MinresState& s, cudaStream_t st) {
@@ -528,7 +535,7 @@ static int minres_iteration(MinresOperator& A, Preconditioner* M, MinresState& s
     }
     {
         ProfScope prof(PROF_MINRES_SCALAR, st);
-        minres_s1_kernel<<<s.P, kScalarThreads, 0, st>>>(s.cs, s.active, s.pb, s.nblk, s.P, s.n_active);
+        minres_s1_kernel<<<s.P, kScalarThreads, 0, st>>>(s.cs, s.active, s.pb, s.nblk, s.P, s.n_active, s.rec, s.rec_k);
     }
     {
         // v = (previous M r2, or r1) / oldb
@@ -558,9 +565,18 @@ static bool graphs_enabled() {
     return !off;
 }
 
+// Optional by-product of a solve: the Lanczos coefficients MINRES computes anyway.  tridiag is [P][k][2] on the
+// host (alfa_j, beta_{j+1} of iteration j; zero past a column's last iteration), beta1 is [P] (||b||, or
+// sqrt(b . M b) with a preconditioner).
+struct LanczosRecord {
+    int k = 0;
+    double* tridiag = nullptr;
+    double* beta1 = nullptr;
+};
+
 static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, long ld, int P, double* X,
                        double tol, int maxiter, int check_every, int* iters, double* resid, int* istop,
-                       cudaStream_t caller_st) {
+                       cudaStream_t caller_st, const LanczosRecord* record = nullptr) {
     LMC_REQUIRE(P >= 1, "need at least one right-hand side");
     LMC_REQUIRE(maxiter >= 1 && check_every >= 1, "maxiter/check_every must be positive");
     const long n = A.n;
@@ -573,8 +589,10 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
     const size_t part_al = (sizeof(double) * (size_t)P * nblk + 255) & ~(size_t)255;
     const size_t cs_al = (sizeof(ColState) * (size_t)P + 255) & ~(size_t)255;
     const size_t col_al = (sizeof(double) * (size_t)P + 255) & ~(size_t)255;
+    const int rec_k = (record && record->tridiag) ? std::min(record->k, maxiter) : 0;
+    const size_t rec_al = (sizeof(double) * (size_t)P * rec_k * 2 + 255) & ~(size_t)255;
     void* ws = nullptr;
-    LMC_TRY(A.workspace(vec_al * nvec + 3 * part_al + cs_al + 2 * col_al + 256, &ws));
+    LMC_TRY(A.workspace(vec_al * nvec + 3 * part_al + cs_al + 2 * col_al + 256 + rec_al, &ws));
     char* base = static_cast<char*>(ws);
     WsSlice bufs[10];
     for (int i = 0; i < nvec; ++i) bufs[i].p = base + vec_al * i;
@@ -592,6 +610,8 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
     s.active = reinterpret_cast<int*>(tail + 3 * part_al + cs_al + col_al);
     s.n_active = reinterpret_cast<int*>(tail + 3 * part_al + cs_al + 2 * col_al);
     s.rtol = std::fmin(1e-10, tol); s.maxiter = maxiter;
+    s.rec = rec_k ? reinterpret_cast<double*>(tail + 3 * part_al + cs_al + 2 * col_al + 256) : nullptr;
+    s.rec_k = rec_k;
     const int* perm = A.perm;
     const dim3 vgrid((unsigned)nblk, (unsigned)P);
     const int sthreads = 128, sblocks = ceil_div(P, sthreads);
@@ -608,6 +628,7 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
         LMC_CHECK(cudaStreamWaitEvent(st, sh->ev_join, 0));
     }
 
+    if (rec_k) LMC_CHECK(cudaMemsetAsync(s.rec, 0, sizeof(double) * (size_t)P * rec_k * 2, st));
     minres_init_kernel<<<vgrid, kVecThreads, 0, st>>>(RHS, ld, perm, n, s.b, s.r2, s.x, s.wa, s.wb, s.wc, s.pa, nblk);
     count_launch();
     if (M) {
@@ -695,13 +716,31 @@ static int minres_core(MinresOperator& A, Preconditioner* M, const double* RHS, 
     LMC_CHECK(cudaGetLastError());
     std::vector<ColState> h((size_t)P);
     LMC_CHECK(cudaMemcpyAsync(h.data(), s.cs, sizeof(ColState) * P, cudaMemcpyDeviceToHost, st));
+    if (rec_k) {
+        // rows of record->k entries on the host, rec_k <= k of them filled
+        LMC_CHECK(cudaMemcpy2DAsync(record->tridiag, sizeof(double) * 2 * record->k, s.rec, sizeof(double) * 2 * rec_k,
+                                    sizeof(double) * 2 * rec_k, P, cudaMemcpyDeviceToHost, st));
+    }
     LMC_CHECK(cudaStreamSynchronize(st));
     for (int c = 0; c < P; ++c) {
+        if (record && record->beta1) record->beta1[c] = h[c].beta1;
         if (iters) iters[c] = h[c].itn;
         if (resid) resid[c] = h[c].resid;
         if (istop) istop[c] = h[c].istop;
     }
     return 0;
+}
+
+int minres_solve_lanczos(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                         int check_every, int* iters, double* resid, int* istop, int k, double* tridiag,
+                         double* beta1, cudaStream_t st) {
+    LMC_REQUIRE(op->Q > 0, "operator parameters not set");
+    LMC_REQUIRE(k >= 1 && tridiag, "need room for at least one Lanczos step");
+    FusedOperator A(op);
+    LanczosRecord rec;
+    rec.k = k; rec.tridiag = tridiag; rec.beta1 = beta1;
+    for (long i = 0; i < (long)P * k * 2; ++i) tridiag[i] = 0.0;
+    return minres_core(A, nullptr, RHS, ld, P, X, tol, maxiter, check_every, iters, resid, istop, st, &rec);
 }
 
 int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,

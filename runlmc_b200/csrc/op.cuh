@@ -101,6 +101,11 @@ int minres_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, doubl
                  int check_every, int* iters, double* resid, int* istop, cudaStream_t st,
                  const double* jacobi = nullptr);
 
+// same solve, also returning the Lanczos tridiagonals the recurrence computes (stochastic Lanczos quadrature)
+int minres_solve_lanczos(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
+                         int check_every, int* iters, double* resid, int* istop, int k, double* tridiag,
+                         double* beta1, cudaStream_t st);
+
 int cg_solve(lmc_op* op, const double* RHS, long ld, int P, double* X, double tol, int maxiter,
              int check_every, int* iters, double* resid, int* info, cudaStream_t st);
 

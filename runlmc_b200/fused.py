@@ -319,6 +319,25 @@ class FusedLMC:
 
     PRECONDITIONERS = {None: 0, 'none': 0, 'jacobi': 1}     # LMC_PRECOND_* of include/lmc_b200.h
 
+    def minres_lanczos_device(self, RHS, k, tol=1e-4, maxiter=None, check_every=100):
+        """minres_device that also returns the Lanczos tridiagonals of the solves (lmc_minres_lanczos):
+        (X, iters, resid, istop, tridiag [P, k, 2], beta1 [P])."""
+        torch = nat.require_cuda()
+        assert RHS.is_cuda and RHS.dtype == torch.float64 and RHS.is_contiguous()
+        P = RHS.shape[0]
+        X = torch.empty_like(RHS)
+        iters = np.zeros(P, dtype=np.int32)
+        resid = np.zeros(P, dtype=np.float64)
+        istop = np.zeros(P, dtype=np.int32)
+        tri = np.zeros((P, int(k), 2), dtype=np.float64)
+        beta1 = np.zeros(P, dtype=np.float64)
+        nat.check(nat.lib.lmc_minres_lanczos(
+            self._h, _dev(RHS), RHS.shape[1], P, _dev(X), float(tol),
+            int(self.n if maxiter is None else maxiter), int(check_every),
+            nat.host_ptr(iters), nat.host_ptr(resid), nat.host_ptr(istop), int(k), nat.host_ptr(tri),
+            nat.host_ptr(beta1), nat.current_stream_ptr()))
+        return X, iters, resid, istop, tri, beta1
+
     def minres_device(self, RHS, tol=1e-4, maxiter=None, check_every=100, precond=None):
         torch = nat.require_cuda()
         assert RHS.is_cuda and RHS.dtype == torch.float64 and RHS.is_contiguous()

@@ -36,13 +36,18 @@ class Metrics:
 class StochasticDerivService:
     """:param metrics: a Metrics instance or None, :param pool: pool for operator
     trees the fused path does not cover, :param n_it: number of probes,
-    :param tol: solver tolerance (stochastic_deriv.py:27-31)."""
+    :param tol: solver tolerance (stochastic_deriv.py:27-31).
+    :param logdet_steps: (extension, default off) keep this many Lanczos steps of every probe solve and
+        attach the stochastic-Lanczos-quadrature estimate of log det K to the result (``log_det_K``,
+        ``log_det_K_stderr``; approx/logdet.py) -- the reference only has a dense Cholesky for it
+        (models/interpolated_llgp.py:262-276).  Fused operators only."""
 
-    def __init__(self, metrics, pool, n_it, tol):
+    def __init__(self, metrics, pool, n_it, tol, logdet_steps=0):
         self.metrics = metrics
         self._pool = pool
         self._n_it = n_it
         self._tol = tol
+        self._logdet_steps = logdet_steps
 
     def generate(self, K, y, rs=None):
         """Draw n_it Rademacher probes from the GLOBAL numpy RNG exactly like the
@@ -53,11 +58,26 @@ class StochasticDerivService:
             rs = np.random.randint(0, 2, (self._n_it, n)) * 2 - 1
         rs = np.asarray(rs)
         RHS = np.vstack([np.asarray(y, dtype=np.float64).reshape(1, -1), rs.astype(np.float64)])
-        X, iters, resid, _ = solve_block(K, RHS, tol=self._tol)
+        fused = fused_of(K) if self._logdet_steps else None
+        logdet = None
+        M = getattr(K, 'preconditioner', None)      # honoured like Iterative.solve does (iterative.py:47)
+        if fused is not None and M is None:
+            from ..approx.logdet import quadrature_terms
+            Xd, iters, resid, _, tri, beta1 = fused.minres_lanczos_device(
+                dev.to_device(RHS), self._logdet_steps, tol=self._tol)
+            X = Xd.cpu().numpy()
+            logdet = quadrature_terms(tri[1:], beta1[1:], iters[1:])      # the probes, not y
+        else:
+            X, iters, resid, _ = solve_block(K, RHS, tol=self._tol, preconditioner=M)
         if self.metrics is not None:
             self.metrics.iterations.append(np.mean(iters))
             self.metrics.solv_error.append(np.mean(resid))
-        return StochasticDeriv(X[0], rs, list(X[1:]), self._n_it)
+        deriv = StochasticDeriv(X[0], rs, list(X[1:]), self._n_it)
+        if logdet is not None and len(logdet):
+            deriv.log_det_K = float(np.mean(logdet))
+            deriv.log_det_K_stderr = float(np.std(logdet, ddof=1) / np.sqrt(len(logdet))) if len(logdet) > 1 \
+                else float('nan')
+        return deriv
 
     def _concurrent_solve(self, ls):
         return self._pool.starmap(Iterative.solve, ls)
@@ -73,6 +93,8 @@ class StochasticDeriv(Derivative):
         self._inv_rs = inv_rs
         self._n_it = n_it
         self._dev_cache = None
+        self.log_det_K = None            # set by a service created with logdet_steps > 0
+        self.log_det_K_stderr = None
 
     def _dev(self):
         if self._dev_cache is None:

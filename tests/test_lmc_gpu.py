@@ -327,3 +327,54 @@ def test_starmap_of_solves_is_one_block_solve():
         assert np.linalg.norm(K.matvec(xr) - r) < 1e-2
     # anything else runs task by task
     assert InlinePool(None).starmap(lambda a, b: a + b, [(1, 2), (3, 4)]) == [3, 7]
+
+
+def test_lanczos_record_and_stochastic_logdet():
+    """lmc_minres_lanczos: the tridiagonals the block solver records are the oracle's (restated scipy loop) --
+    tightly while Lanczos is still reproducible, and as a quadrature at convergence -- and the log-det estimate
+    built from them matches the oracle's estimate on the same probes and the dense log det within its own
+    standard error."""
+    import torch
+    import oracle.lmc_oracle as orc
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.approx.iterative import fused_of
+    from runlmc_b200.approx.logdet import stochastic_logdet, quadrature_terms
+    from test_oracle_golden import oracle_operator
+    prob, _ = golden_problem('lmc_A')
+    fk, dists, interps, ad = build(prob)
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    _, ref = oracle_operator(prob)
+    n = prob.n
+    rng = np.random.default_rng(11)
+    probes = rng.integers(0, 2, (24, n)) * 2.0 - 1.0
+    fused = fused_of(K)
+    R = torch.as_tensor(probes, device='cuda')
+    # (a) first steps against the oracle's record
+    _, iters, _, _, tri, beta1 = fused.minres_lanczos_device(R[:3].contiguous(), 7, tol=1e-4, maxiter=7)
+    for c in range(3):
+        rec = []
+        orc.minres(ref.matvec, probes[c], 1e-10, 7, record=rec)
+        assert abs(beta1[c] - rec[0]) < 1e-12 * rec[0]
+        want = np.array(rec[1:])
+        assert np.abs(tri[c, :len(want)] - want).max() / np.abs(want).max() < 1e-10
+    # (b) a record shorter than the solve keeps the first k steps; a longer one is zero past the last iteration
+    _, iters, _, _, tri_s, _ = fused.minres_lanczos_device(R[:3].contiguous(), 5, tol=1e-4, maxiter=7)
+    assert np.array_equal(tri_s, tri[:, :5])
+    _, iters_f, _, _, tri_f, b1_f = fused.minres_lanczos_device(R[:3].contiguous(), 4000, tol=1e-4)
+    for c in range(3):
+        assert 0 < iters_f[c] < 4000 and not tri_f[c, iters_f[c]:].any() and tri_f[c, iters_f[c] - 1].all()
+    # (c) the estimate
+    est, err, terms = stochastic_logdet(K, probes=probes)
+    want_est, want_terms = orc.stochastic_logdet(ref.matvec, probes, 1e-10, n)
+    assert np.abs(terms - want_terms).max() < 1e-6 * np.abs(want_terms).max()
+    sign, logdet = np.linalg.slogdet(ref.dense())
+    assert sign > 0 and abs(est - logdet) < 4 * err + 1e-3 * abs(logdet)
+    assert len(quadrature_terms(tri_f, b1_f, iters_f)) == 3
+    with pytest.raises(ValueError):
+        stochastic_logdet(object())
+    # (d) as a by-product of the derivative service's own probe solves
+    from runlmc_b200.lmc.stochastic_deriv import StochasticDerivService
+    deriv = StochasticDerivService(None, None, len(probes), 1e-4, logdet_steps=4000).generate(K, prob.y, rs=probes)
+    assert abs(deriv.log_det_K - est) < 1e-9 * abs(est) and abs(deriv.log_det_K_stderr - err) < 1e-6 * err
+    plain = StochasticDerivService(None, None, len(probes), 1e-4).generate(K, prob.y, rs=probes)
+    assert plain.log_det_K is None and np.array_equal(plain.alpha, deriv.alpha)
