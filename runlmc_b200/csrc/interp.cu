@@ -996,6 +996,168 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_v3_kernel(const InterpArg
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same gather writing a point-major block (out[point][column], caller's rows) itself.  Threads own
+// points as above, so the 2 GP results of a point and pass sit in ONE thread while a row piece wants them
+// side by side in GP lanes: an 8 x 8 transpose across each group of 8 lanes (three butterfly stages of
+// __shfl_xor) turns "lane = point, registers = pairs" into "lane = pair, registers = 8 points", after which
+// the 8 lanes of a group store 128 contiguous bytes of one row -- and read the 128 bytes of the input row
+// next to them for the noise term.  No transposing pass, no scratch copy of the result.
+// ---------------------------------------------------------------------------
+template <int GP, int TB>
+__global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpArgs a, int passes_per_cta) {
+    static_assert(GP == 8, "one pair per lane of an 8-lane group");
+    typedef Gather3Smem<GP, TB> Smem;
+    constexpr int W = Smem::W;
+    extern __shared__ __align__(16) unsigned char smem_raw5[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw5);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x % a.tiles;
+    const int d = blockIdx.x / a.tiles;
+    const int mx = a.m0, my = a.m1;
+    const int BX0 = (tile / a.tiles1) * TB, BY0 = (tile % a.tiles1) * TB;
+    const int X0 = BX0 - 3, Y0 = BY0 - 3;
+    const int* bs = a.bin_start + (long)d * a.NB;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    const int pair_lo = blockIdx.y * passes_per_cta * GP;
+    const int pair_hi = min(npairs_tot, pair_lo + passes_per_cta * GP);
+    if (tid < TB) {
+        const int bx = BX0 + tid;
+        int beg = 0, end = 0;
+        if (bx < a.nb0) {
+            beg = bs[(long)bx * a.nb1 + BY0];
+            end = bs[(long)bx * a.nb1 + min(BY0 + TB, a.nb1)];
+        }
+        s.row_beg[tid] = beg;
+        s.row_off[tid + 1] = end - beg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s.row_off[0] = 0;
+        for (int r = 0; r < TB; ++r) s.row_off[r + 1] += s.row_off[r];
+    }
+    __syncthreads();
+    const int npts = s.row_off[TB];
+    if (npts == 0) return;
+
+    auto stage = [&](int pbase, int buf) {
+        for (int p = 0; p < GP; ++p) {
+            const int pair = pbase + p;
+            if (pair >= pair_hi) break;
+            const cplx* gsl = a.Gc + ((long)pair * a.D + d) * a.grid_pitch;
+            for (int c = tid; c < W * W; c += 256) {
+                const int x = c / W, y = c - x * W;
+                const int gx = clampi(X0 + x, 0, mx - 1), gy = clampi(Y0 + y, 0, my - 1);
+                cp_async16(&s.cell[buf][p][c], gsl + (long)gx * my + gy);
+            }
+        }
+        cp_async_commit();
+    };
+    stage(pair_lo, 0);
+
+    double wx[2][4], wy[2][4];
+    int o0[2], so[2];
+    bool have[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int li = tid + 256 * q;
+        have[q] = li < npts;
+        so[q] = 0;
+        if (have[q]) {
+            int r = 0;
+            while (li >= s.row_off[r + 1]) ++r;
+            const long gi = s.row_beg[r] + (li - s.row_off[r]);
+            keys_weights(a.u0[gi], wx[q]);
+            keys_weights(a.u1[gi], wy[q]);
+            const int ix0 = a.i00[gi] - 1, iy0 = a.i01[gi] - 1;
+            o0[q] = (ix0 - X0) * W + (iy0 - Y0);
+            so[q] = a.perm_out ? a.perm_out[gi] : (int)gi;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wx[q][k] = wy[q][k] = 0.0;
+            o0[q] = 0;
+        }
+    }
+    const double nz = a.noise ? a.noise[d] : 0.0;
+    const int lane = tid & 31, gb = lane & ~7, g = lane & 7;
+    const double* __restrict__ xin = a.in_rows;
+    double* __restrict__ yout = a.out;
+
+    int buf = 0;
+    for (int pbase = pair_lo; pbase < pair_hi; pbase += GP, buf ^= 1) {
+        if (pbase + GP < pair_hi) { stage(pbase + GP, buf ^ 1); cp_async_wait_1(); }
+        else cp_async_wait_all();
+        __syncthreads();
+        const int np = min(GP, pair_hi - pbase);       // uniform over the CTA
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned hv = __ballot_sync(0xffffffffu, have[q]);
+            if (hv == 0) continue;                     // uniform over the warp
+            double acc[GP][2];
+#pragma unroll
+            for (int p = 0; p < GP; ++p) {
+                double r0s = 0.0, r1s = 0.0;
+                if (p < np) {
+                    const cplx* cq = s.cell[buf][p] + o0[q];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const cplx v = cq[k * W + j];
+                            r0 = fma(wy[q][j], v.x, r0);
+                            r1 = fma(wy[q][j], v.y, r1);
+                        }
+                        r0s = fma(wx[q][k], r0, r0s);
+                        r1s = fma(wx[q][k], r1, r1s);
+                    }
+                }
+                acc[p][0] = r0s;
+                acc[p][1] = r1s;
+            }
+            // 8 x 8 transpose across the lane group: afterwards acc[i] belongs to point (gb + i), pair pbase + g
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+                const bool up = (g & sft) != 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i & sft) continue;
+                    const double sx = up ? acc[i][0] : acc[i | sft][0];
+                    const double sy = up ? acc[i][1] : acc[i | sft][1];
+                    const double rx = __shfl_xor_sync(0xffffffffu, sx, sft);
+                    const double ry = __shfl_xor_sync(0xffffffffu, sy, sft);
+                    if (up) { acc[i][0] = rx; acc[i][1] = ry; }
+                    else { acc[i | sft][0] = rx; acc[i | sft][1] = ry; }
+                }
+            }
+            const int pair = pbase + g;
+            const int cA = 2 * pair;
+            const bool okA = pair < pair_hi, okB = okA && cA + 1 < a.ncols;
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) {
+                long row[4];
+                double x0[4], x1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    row[i] = __shfl_sync(0xffffffffu, so[q], gb + h + i);
+                    const bool live = (hv >> (gb + h + i)) & 1u;
+                    x0[i] = (a.noise && live && okA) ? __ldcs(xin + row[i] * a.ldr + cA) : 0.0;
+                    x1[i] = (a.noise && live && okB) ? __ldcs(xin + row[i] * a.ldr + cA + 1) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool live = (hv >> (gb + h + i)) & 1u;
+                    double v0 = acc[h + i][0], v1 = acc[h + i][1];
+                    if (a.noise) { v0 = fma(nz, x0[i], v0); v1 = fma(nz, x1[i], v1); }
+                    if (live && okA) __stcs(yout + row[i] * a.ldo + cA, v0);
+                    if (live && okB) __stcs(yout + row[i] * a.ldo + cA + 1, v1);
+                }
+            }
+        }
+        __syncthreads();   // buffer `buf` is free for the pass after next
+    }
+}
+
 // out[c][i] = in[c][perm[i]]: with perm = sorted -> caller it brings a block of caller-ordered columns
 // into the operator's sorted point order ahead of the (coalesced) sorted-order kernels, with the
 // inverse permutation it takes results back.  Writes are coalesced; the source column (8 n bytes)
@@ -1181,6 +1343,7 @@ static InterpArgs make_args(const PointSet& ps, const ColumnView& cv) {
     a.out_start = ps.out_start_dev;
     a.in = cv.in; a.out = cv.out; a.ld = cv.ld; a.ldo = cv.ld_out ? cv.ld_out : cv.ld;
     if (cv.rows_in) { a.in_rows = cv.in; a.ldr = cv.ld; a.in = nullptr; }
+    if (cv.rows_out) a.perm_out = ps.identity ? nullptr : ps.perm;
     a.ncols = cv.ncols;
     a.in_scale = cv.in_scale; a.active = cv.active;
     a.grid_pitch = ps.grid_pitch;
@@ -1341,9 +1504,16 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
     return 0;
 }
 
+bool from_grid_writes_rows(const PointSet& ps) {
+    static const bool off = getenv("LMC_NO_ROWS_GATHER") != nullptr;
+    static const int variant = env_int("LMC_FROMGRID2D", 3);
+    return !off && ps.ndim == 2 && variant >= 3 && ps.max_gather_tile_pts <= 512;
+}
+
 int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const double* noise,
               cudaStream_t st) {
     if (cv.ncols == 0) return 0;
+    if (cv.rows_out) LMC_REQUIRE(ps.ndim == 2, "point-major output: 2-D gather only");
     InterpArgs a = make_args(ps, cv);
     a.Gc = G;
     ProfScope prof(PROF_FROM_GRID, st);
@@ -1361,7 +1531,20 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
     } else {
         static const int variant = env_int("LMC_FROMGRID2D", 3);
         constexpr int GP = 8, TB = 16;
-        if (variant >= 3 && ps.max_gather_tile_pts <= 512) {
+        if (cv.rows_out) {
+            LMC_REQUIRE(from_grid_writes_rows(ps) && cv.rows_in, "point-major output not supported by this gather");
+            typedef Gather3Smem<GP, TB> Smem;
+            static bool attr_r = false;
+            if (!attr_r) { LMC_TRY(set_smem(from_grid_2d_rows_kernel<GP, TB>, sizeof(Smem))); attr_r = true; }
+            a.tiles1 = ceil_div(ps.nb[1], TB);
+            a.tiles = ceil_div(ps.nb[0], TB) * a.tiles1;
+            const long ctas1 = (long)a.tiles * ps.D;
+            const int npass = ceil_div(npairs, GP);
+            int ppc = npass;
+            while (ppc > 1 && ctas1 * ceil_div(npass, ppc) < 148L * 2 * 4) ppc = (ppc + 1) / 2;
+            dim3 grid((unsigned)ctas1, (unsigned)ceil_div(npass, ppc));
+            from_grid_2d_rows_kernel<GP, TB><<<grid, 256, sizeof(Smem), st>>>(a, ppc);
+        } else if (variant >= 3 && ps.max_gather_tile_pts <= 512) {
             typedef Gather3Smem<GP, TB> Smem;
             static bool attr = false;
             if (!attr) { LMC_TRY(set_smem(from_grid_2d_v3_kernel<GP, TB>, sizeof(Smem))); attr = true; }

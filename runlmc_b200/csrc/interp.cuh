@@ -50,7 +50,8 @@ struct ColumnView {
     bool sorted_in = false;            // `in` already is in the operator's sorted point order
     bool sorted_out = false;           // `out` is wanted in sorted order
     bool rows_in = false;              // `in` is point-major: in[point][column], row stride ld, caller's order
-                                       // (to_grid only, where to_grid_takes_rows() says so)
+                                       // (to_grid where to_grid_takes_rows() says so; from_grid with rows_out)
+    bool rows_out = false;             // `out` is point-major too (from_grid where from_grid_writes_rows())
 };
 
 // block of columns between the caller's point order and the sorted order (out[c][i] = in[c][p[i]],
@@ -63,6 +64,7 @@ int rows_to_sorted_cols(const PointSet& ps, const double* rows, long ldr, int nc
 int sorted_cols_to_rows(const PointSet& ps, const double* cols, long ldc, int ncols, const double* noise,
                         const double* rows_in, long ldi, double* rows_out, long ldo, cudaStream_t st);
 bool to_grid_takes_rows(const PointSet& ps, int ncols);
+bool from_grid_writes_rows(const PointSet& ps);
 // G[pair][d][cell] (complex pairs of columns 2p, 2p+1)  <-  W^T in     (deterministic, no atomics)
 int to_grid(const PointSet& ps, const ColumnView& cv, cplx* G, cudaStream_t st);
 // out = W G (+ noise_d * in when noise != nullptr)

@@ -160,9 +160,17 @@ int op_mvm_rows(lmc_op* op, const double* X, long ldx, int P, double* Y, long ld
         LMC_TRY(to_grid(op->ps, t, op->G, st));
         LMC_TRY(op_grid_block(op, op->G, cnt, st));
         ColumnView u;
-        u.out = op->Vs; u.ld = u.ld_out = n; u.ncols = t.ncols; u.sorted_in = u.sorted_out = true;
-        LMC_TRY(from_grid(op->ps, u, op->G, nullptr, st));
-        LMC_TRY(sorted_cols_to_rows(op->ps, op->Vs, n, t.ncols, op->noise, X + c0, ldx, Y + c0, ldy, st));
+        u.ncols = t.ncols;
+        if (from_grid_writes_rows(op->ps)) {
+            // the gather writes the caller's rows itself and reads X's rows beside them for the noise term
+            u.in = X + c0; u.ld = ldx; u.rows_in = true;
+            u.out = Y + c0; u.ld_out = ldy; u.rows_out = true;
+            LMC_TRY(from_grid(op->ps, u, op->G, op->noise, st));
+        } else {
+            u.out = op->Vs; u.ld = u.ld_out = n; u.sorted_in = u.sorted_out = true;
+            LMC_TRY(from_grid(op->ps, u, op->G, nullptr, st));
+            LMC_TRY(sorted_cols_to_rows(op->ps, op->Vs, n, t.ncols, op->noise, X + c0, ldx, Y + c0, ldy, st));
+        }
     }
     return 0;
 }
