@@ -271,7 +271,6 @@ template <int G, int CAP>
 struct Scatter1Smem {
     double2 w[CAP][2];            // Keys weights of the 4 taps
     double v[2][CAP * (G + 1)];   // reused for the partial sums
-    int src[CAP];                 // point-major input: the caller's row of every staged point
 };
 
 template <int G, int CAP, bool ROWS>
@@ -306,19 +305,43 @@ __global__ void __launch_bounds__(256, CAP <= 256 ? 4 : 2) to_grid_1d_v3_kernel(
 
     for (int chunk = pbeg; chunk < pend; chunk += CAP) {
         const int cnt = min(CAP, pend - chunk);
-        for (int i = tid; i < cnt; i += 256) {
-            const int gi = chunk + i;
-            double w[4];
-            keys_weights(a.u0[gi], w);
-            s.w[i][0] = make_double2(w[0], w[1]);
-            s.w[i][1] = make_double2(w[2], w[3]);
-            const long src = a.perm_in ? (long)a.perm_in[gi] : (long)gi;
-            if (ROWS) s.src[i] = (int)src;
-            else stage_point_values<G, CAP>(s.v[0], i, a.in + (long)col0 * a.ld + src, a.ld, ncol);
-        }
         if (ROWS) {
-            __syncthreads();
-            stage_rows<G, CAP>(s.v[0], s.src, cnt, a.in_rows + col0, a.ldr, ncol, false, tid);
+            // a warp stages its own 32 points: weights by the owning lane, values by groups of 2 G lanes that
+            // copy one point's 16 G contiguous bytes each (row index handed round by shuffle)
+            constexpr int VP1 = G + 1, LPP = 2 * G, PPW = 32 / LPP;
+            const int lane = tid & 31, sub = lane / LPP, c = lane % LPP;
+            double* dst0 = s.v[0] + (c & 1) * (CAP * VP1) + (c >> 1);
+            for (int ib = (tid & ~31); ib < cnt; ib += 256) {
+                const int i = ib + lane;
+                long src = 0;
+                if (i < cnt) {
+                    const int gi = chunk + i;
+                    double w[4];
+                    keys_weights(a.u0[gi], w);
+                    s.w[i][0] = make_double2(w[0], w[1]);
+                    s.w[i][1] = make_double2(w[2], w[3]);
+                    src = a.perm_in ? (long)a.perm_in[gi] : (long)gi;
+                }
+#pragma unroll 4
+                for (int t = 0; t < 32; t += PPW) {
+                    const long r = __shfl_sync(0xffffffffu, src, t + sub);
+                    const int j = ib + t + sub;
+                    if (j < cnt) {
+                        if (c < ncol) cp_async8(dst0 + j * VP1, a.in_rows + r * a.ldr + col0 + c);
+                        else dst0[j * VP1] = 0.0;
+                    }
+                }
+            }
+        } else {
+            for (int i = tid; i < cnt; i += 256) {
+                const int gi = chunk + i;
+                double w[4];
+                keys_weights(a.u0[gi], w);
+                s.w[i][0] = make_double2(w[0], w[1]);
+                s.w[i][1] = make_double2(w[2], w[3]);
+                const long src = a.perm_in ? (long)a.perm_in[gi] : (long)gi;
+                stage_point_values<G, CAP>(s.v[0], i, a.in + (long)col0 * a.ld + src, a.ld, ncol);
+            }
         }
         cp_async_commit();
         cp_async_wait_all();
@@ -432,6 +455,106 @@ __global__ void __launch_bounds__(256) from_grid_1d_v3_kernel(const InterpArgs a
             if (actA[u]) a.out[(long)cA * a.ldo + so] = oA;
             if (actB[u]) a.out[(long)cB * a.ldo + so] = oB;
         }
+    }
+}
+
+// 8 x 8 transpose across each group of 8 lanes: before, lane t of a group holds acc[p] = element (t, p);
+// afterwards acc[i] = element (i, g) for its own position g in the group.  Three butterfly stages of
+// __shfl_xor, every register index a compile-time constant.
+__device__ __forceinline__ void lane_group_transpose8(double (&acc)[8][2], int g) {
+#pragma unroll
+    for (int sft = 1; sft < 8; sft <<= 1) {
+        const bool up = (g & sft) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i & sft) continue;
+            const double sx = up ? acc[i][0] : acc[i | sft][0];
+            const double sy = up ? acc[i][1] : acc[i | sft][1];
+            const double rx = __shfl_xor_sync(0xffffffffu, sx, sft);
+            const double ry = __shfl_xor_sync(0xffffffffu, sy, sft);
+            if (up) { acc[i][0] = rx; acc[i][1] = ry; }
+            else { acc[i | sft][0] = rx; acc[i | sft][1] = ry; }
+        }
+    }
+}
+
+// Row pieces of 8 points after the transpose: lane g of a group holds pair `pair` of the points whose rows
+// the lanes gb .. gb + 7 own (row index `so`, liveness bit in `hv`); 8 lanes store 128 contiguous bytes
+// of one row and read the input row beside them for the noise term.
+__device__ __forceinline__ void store_row_pieces8(const double (&acc)[8][2], int so, unsigned hv, int gb, int cA,
+                                                  bool okA, bool okB, bool noise, double nz,
+                                                  const double* __restrict__ xin, long ldr,
+                                                  double* __restrict__ yout, long ldo) {
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        long row[4];
+        double x0[4], x1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            row[i] = __shfl_sync(0xffffffffu, so, gb + h + i);
+            const bool live = (hv >> (gb + h + i)) & 1u;
+            x0[i] = (noise && live && okA) ? __ldcs(xin + row[i] * ldr + cA) : 0.0;
+            x1[i] = (noise && live && okB) ? __ldcs(xin + row[i] * ldr + cA + 1) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool live = (hv >> (gb + h + i)) & 1u;
+            double v0 = acc[h + i][0], v1 = acc[h + i][1];
+            if (noise) { v0 = fma(nz, x0[i], v0); v1 = fma(nz, x1[i], v1); }
+            if (live && okA) __stcs(yout + row[i] * ldo + cA, v0);
+            if (live && okB) __stcs(yout + row[i] * ldo + cA + 1, v1);
+        }
+    }
+}
+
+// 1-D gather writing a point-major block (out[point][column], the caller's rows): results of 8 pairs per
+// point, transposed across each group of 8 lanes, leave as 128-byte row pieces (see the 2-D variant below).
+__global__ void __launch_bounds__(256) from_grid_1d_rows_kernel(const InterpArgs a, int pairs_per_cta) {
+    const int d = blockIdx.y;
+    const long end = a.out_start[d + 1];
+    const long i_raw = a.out_start[d] + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i_raw < end;
+    const unsigned hv = __ballot_sync(0xffffffffu, have);
+    if (hv == 0) return;
+    const long i = have ? i_raw : end - 1;           // idle lanes shadow a live point and store nothing
+    const int m = a.m0;
+    const int npairs_tot = (a.ncols + 1) >> 1;
+    double w[4];
+    keys_weights(a.u0[i], w);
+    const int i0 = a.i00[i];
+    int cell[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) cell[t] = clampi(i0 - 1 + t, 0, m - 1);
+    const int so = a.perm_out ? a.perm_out[i] : (int)i;
+    const double nz = a.noise ? a.noise[d] : 0.0;
+    const int pair0 = blockIdx.z * pairs_per_cta;
+    const int pair1 = min(npairs_tot, pair0 + pairs_per_cta);
+    const cplx* gbase = a.Gc + (long)d * a.grid_pitch;
+    const long pstride = (long)a.D * a.grid_pitch;
+    const int lane = threadIdx.x & 31, gb = lane & ~7, g = lane & 7;
+    for (int pc = pair0; pc < pair1; pc += 8) {
+        double acc[8][2];
+#pragma unroll
+        for (int hf = 0; hf < 8; hf += 4) {
+            cplx v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pair = min(pc + hf + u, pair1 - 1);
+                const cplx* gp = gbase + pair * pstride;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[u][t] = __ldg(gp + cell[t]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[hf + u][0] = fma(w[3], v[u][3].x, fma(w[2], v[u][2].x, fma(w[1], v[u][1].x, w[0] * v[u][0].x)));
+                acc[hf + u][1] = fma(w[3], v[u][3].y, fma(w[2], v[u][2].y, fma(w[1], v[u][1].y, w[0] * v[u][0].y)));
+            }
+        }
+        lane_group_transpose8(acc, g);
+        const int pair = pc + g;
+        const int cA = 2 * pair;
+        const bool okA = pair < pair1, okB = okA && cA + 1 < a.ncols;
+        store_row_pieces8(acc, so, hv, gb, cA, okA, okB, a.noise != nullptr, nz, a.in_rows, a.ldr, a.out, a.ldo);
     }
 }
 
@@ -1115,44 +1238,11 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpA
                 acc[p][0] = r0s;
                 acc[p][1] = r1s;
             }
-            // 8 x 8 transpose across the lane group: afterwards acc[i] belongs to point (gb + i), pair pbase + g
-#pragma unroll
-            for (int sft = 1; sft < 8; sft <<= 1) {
-                const bool up = (g & sft) != 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (i & sft) continue;
-                    const double sx = up ? acc[i][0] : acc[i | sft][0];
-                    const double sy = up ? acc[i][1] : acc[i | sft][1];
-                    const double rx = __shfl_xor_sync(0xffffffffu, sx, sft);
-                    const double ry = __shfl_xor_sync(0xffffffffu, sy, sft);
-                    if (up) { acc[i][0] = rx; acc[i][1] = ry; }
-                    else { acc[i | sft][0] = rx; acc[i | sft][1] = ry; }
-                }
-            }
+            lane_group_transpose8(acc, g);     // acc[i] now belongs to point (gb + i), pair pbase + g
             const int pair = pbase + g;
             const int cA = 2 * pair;
             const bool okA = pair < pair_hi, okB = okA && cA + 1 < a.ncols;
-#pragma unroll
-            for (int h = 0; h < 8; h += 4) {
-                long row[4];
-                double x0[4], x1[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    row[i] = __shfl_sync(0xffffffffu, so[q], gb + h + i);
-                    const bool live = (hv >> (gb + h + i)) & 1u;
-                    x0[i] = (a.noise && live && okA) ? __ldcs(xin + row[i] * a.ldr + cA) : 0.0;
-                    x1[i] = (a.noise && live && okB) ? __ldcs(xin + row[i] * a.ldr + cA + 1) : 0.0;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool live = (hv >> (gb + h + i)) & 1u;
-                    double v0 = acc[h + i][0], v1 = acc[h + i][1];
-                    if (a.noise) { v0 = fma(nz, x0[i], v0); v1 = fma(nz, x1[i], v1); }
-                    if (live && okA) __stcs(yout + row[i] * a.ldo + cA, v0);
-                    if (live && okB) __stcs(yout + row[i] * a.ldo + cA + 1, v1);
-                }
-            }
+            store_row_pieces8(acc, so[q], hv, gb, cA, okA, okB, a.noise != nullptr, nz, xin, a.ldr, yout, a.ldo);
         }
         __syncthreads();   // buffer `buf` is free for the pass after next
     }
@@ -1507,13 +1597,14 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
 bool from_grid_writes_rows(const PointSet& ps) {
     static const bool off = getenv("LMC_NO_ROWS_GATHER") != nullptr;
     static const int variant = env_int("LMC_FROMGRID2D", 3);
-    return !off && ps.ndim == 2 && variant >= 3 && ps.max_gather_tile_pts <= 512;
+    if (off) return false;
+    return ps.ndim == 1 || (ps.ndim == 2 && variant >= 3 && ps.max_gather_tile_pts <= 512);
 }
 
 int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const double* noise,
               cudaStream_t st) {
     if (cv.ncols == 0) return 0;
-    if (cv.rows_out) LMC_REQUIRE(ps.ndim == 2, "point-major output: 2-D gather only");
+    if (cv.rows_out) LMC_REQUIRE(from_grid_writes_rows(ps) && cv.rows_in, "point-major output not supported by this gather");
     InterpArgs a = make_args(ps, cv);
     a.Gc = G;
     ProfScope prof(PROF_FROM_GRID, st);
@@ -1526,13 +1617,14 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
         const long ctas1 = (long)ceil_div(maxlen, 256) * ps.D;
         int ppc = npairs;   // all pairs per thread (weights once) unless that underfills the machine
         while (ppc > 1 && ctas1 * ceil_div(npairs, ppc) < 148L * 8) ppc = (ppc + 1) / 2;
+        if (cv.rows_out) ppc = ceil_div(ppc, 8) * 8;      // whole groups of 8 pairs per CTA
         dim3 grid((unsigned)ceil_div(maxlen, 256), (unsigned)ps.D, (unsigned)ceil_div(npairs, ppc));
-        from_grid_1d_v3_kernel<<<grid, 256, 0, st>>>(a, ppc);
+        if (cv.rows_out) from_grid_1d_rows_kernel<<<grid, 256, 0, st>>>(a, ppc);
+        else from_grid_1d_v3_kernel<<<grid, 256, 0, st>>>(a, ppc);
     } else {
         static const int variant = env_int("LMC_FROMGRID2D", 3);
         constexpr int GP = 8, TB = 16;
         if (cv.rows_out) {
-            LMC_REQUIRE(from_grid_writes_rows(ps) && cv.rows_in, "point-major output not supported by this gather");
             typedef Gather3Smem<GP, TB> Smem;
             static bool attr_r = false;
             if (!attr_r) { LMC_TRY(set_smem(from_grid_2d_rows_kernel<GP, TB>, sizeof(Smem))); attr_r = true; }
