@@ -507,6 +507,18 @@ __device__ __forceinline__ void store_row_pieces8(const double (&acc)[8][2], int
     }
 }
 
+// The input-row pieces store_row_pieces8 is going to read, requested into L2 ahead of the tap arithmetic
+// (no registers held; the two end lanes of a group cover the 128-byte piece).
+__device__ __forceinline__ void prefetch_row_pieces8(int so, unsigned hv, int gb, int g, int cA, bool okA,
+                                                     const double* __restrict__ xin, long ldr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long row = __shfl_sync(0xffffffffu, so, gb + i);
+        if ((g == 0 || g == 7) && okA && ((hv >> (gb + i)) & 1u))
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + row * ldr + cA));
+    }
+}
+
 // 1-D gather writing a point-major block (out[point][column], the caller's rows): results of 8 pairs per
 // point, transposed across each group of 8 lanes, leave as 128-byte row pieces (see the 2-D variant below).
 __global__ void __launch_bounds__(256) from_grid_1d_rows_kernel(const InterpArgs a, int pairs_per_cta) {
@@ -1205,6 +1217,7 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpA
     const int lane = tid & 31, gb = lane & ~7, g = lane & 7;
     const double* __restrict__ xin = a.in_rows;
     double* __restrict__ yout = a.out;
+    const bool no_prefetch = a.extra != 0;             // A/B switch (LMC_NO_ROWPREFETCH)
 
     int buf = 0;
     for (int pbase = pair_lo; pbase < pair_hi; pbase += GP, buf ^= 1) {
@@ -1216,6 +1229,8 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpA
         for (int q = 0; q < 2; ++q) {
             const unsigned hv = __ballot_sync(0xffffffffu, have[q]);
             if (hv == 0) continue;                     // uniform over the warp
+            if (a.noise && !no_prefetch)
+                prefetch_row_pieces8(so[q], hv, gb, g, 2 * (pbase + g), pbase + g < pair_hi, xin, a.ldr);
             double acc[GP][2];
 #pragma unroll
             for (int p = 0; p < GP; ++p) {
@@ -1635,6 +1650,8 @@ int from_grid(const PointSet& ps, const ColumnView& cv, const cplx* G, const dou
             int ppc = npass;
             while (ppc > 1 && ctas1 * ceil_div(npass, ppc) < 148L * 2 * 4) ppc = (ppc + 1) / 2;
             dim3 grid((unsigned)ctas1, (unsigned)ceil_div(npass, ppc));
+            static const int no_pf = env_int("LMC_NO_ROWPREFETCH", 0);
+            a.extra = no_pf;
             from_grid_2d_rows_kernel<GP, TB><<<grid, 256, sizeof(Smem), st>>>(a, ppc);
         } else if (variant >= 3 && ps.max_gather_tile_pts <= 512) {
             typedef Gather3Smem<GP, TB> Smem;

@@ -3,6 +3,7 @@
 `ncu --profile-from-start off` captures (see tools/ncu_step.sh).
 
     python tools/one_step.py E mvm            # block product, caller's order
+    python tools/one_step.py E mvm_rows       # block product, caller's order, point-major [n, P] block
     python tools/one_step.py E mvm_sorted     # block product, operator's sorted order
     python tools/one_step.py D minres 2       # K solver iterations
     python tools/one_step.py E grad           # gradient contractions
@@ -33,6 +34,10 @@ def main():
     out = torch.empty_like(V)
     if mode == 'mvm':
         fn = lambda: op.mvm_device(V, out)
+    elif mode == 'mvm_rows':
+        X = V.t().contiguous()
+        Y = torch.empty_like(X)
+        fn = lambda: op.matmat_device(X, Y)
     elif mode == 'mvm_sorted':
         fn = lambda: op.mvm_sorted_device(V, out)
     elif mode == 'minres':
