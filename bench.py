@@ -211,10 +211,10 @@ def family_bytes(family, prob, P, bins, gpitch, rows=False):
     if family == 'to_grid':
         return 8.0 * n * P + 8.0 * d * n + slab * gpitch
     if family == 'from_grid':
-        # point-major blocks: the noise term moves to the transposing pass, the gather only writes
-        return (8.0 if rows else 16.0) * n * P + 8.0 * d * n + slab * gpitch
+        return 16.0 * n * P + 8.0 * d * n + slab * gpitch
     if family == 'other' and rows:
-        # one transposing pass: sorted column-major result + the caller's rows of X in, rows of Y out
+        # point-major blocks whose gather cannot write rows itself (no such geometry among the benchmark
+        # workloads): one transposing pass, sorted column-major result + the caller's rows of X in, rows of Y out
         return 24.0 * n * P + 4.0 * n
     if family == 'other':
         # the two permutation passes of the caller-order product (caller -> sorted before the scatter,
@@ -380,7 +380,10 @@ def small_config_row(name, peak):
     V = torch.as_tensor(Vh, device='cuda')
     OUT = torch.empty_like(V)
     steps = 20 if prob.n >= 100000 else 200
-    ms = timed_product(op, V, OUT, steps, 3, torch.cuda.synchronize, min_warm_s=0.1) / steps
+    X = V.t().contiguous()                 # point-major block, like the headline row
+    Y = torch.empty_like(X)
+    ms = timed_product(lambda: op.matmat_device(X, Y), steps, 3, torch.cuda.synchronize, min_warm_s=0.1) / steps
+    ms_cols = timed_product(lambda: op.mvm_device(V, OUT), steps, 3, torch.cuda.synchronize, min_warm_s=0.1) / steps
     perm = torch.as_tensor(op.perm().astype(np.int64), device='cuda')
     Vs = V[:, perm].contiguous()
     for _ in range(3):
@@ -412,9 +415,9 @@ def small_config_row(name, peak):
     for c in range(ncpu):
         orc.minres(ref.matvec, Vh[c], 1e-10, K)
     dcpu = time.perf_counter() - t0
-    par = parity_check(op, ref, Vh, op.mvm_device(V))
+    par = parity_check(op, ref, Vh, op.matmat_device(X).t())
     return {'workload': workload_desc(name, prob)['workload'], 'mvm_rhs_per_s': P / ms * 1e3, 'ms_per_step': ms,
-            'ms_per_step_sorted_order': ms_sorted,
+            'ms_per_step_column_major': ms_cols, 'ms_per_step_sorted_order': ms_sorted,
             'roofline_mvm': {'bound': 'hbm', 'alg_bytes_per_step': b_mvm, 'achieved': b_mvm / ms / 1e6, 'peak': peak,
                              'unit': 'GB/s', 'frac': b_mvm / ms / 1e6 / peak,
                              'frac_sorted_order': b_mvm / ms_sorted / 1e6 / peak},

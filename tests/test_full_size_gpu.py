@@ -187,3 +187,25 @@ def test_full_size_solver_residuals(full):
     assert (itc == 25).all() and (info == 25).all()
     truec = np.linalg.norm(Bh - op.mvm(Xc), axis=1)
     assert np.allclose(rc, truec, rtol=1e-9)
+
+
+def test_bench_line_contract():
+    """bench.py end to end on a small workload (every leg but the CPU baseline): one JSON line with the
+    contract's keys, parity green, secondary workload rows present."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--workload', 'C', '--steps', '5',
+                          '--warmup', '3', '--no-cpu', '--no-ill'], capture_output=True, text=True, timeout=900,
+                         cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'parity', 'layouts', 'configs'):
+        assert key in line, key
+    assert line['value'] > 0 and line['gpu_launches'] > 0 and line['parity']['ok']
+    assert line['layouts']['max_abs_diff_between_layouts'] == 0.0
+    assert sorted(c['workload'][0] for c in line['configs']) == ['A', 'B', 'D']
+    assert all(c['parity']['ok'] for c in line['configs'])
