@@ -32,6 +32,9 @@ def main():
         Vh = np.vstack([prob.y[None], prob.probes])
         V = torch.as_tensor(Vh, device='cuda')
         KV = op.mvm_device(V)
+        KR = op.matmat_device(V.t().contiguous())      # point-major block: row staging, row-writing gathers
+        assert torch.equal(KR.t(), KV)
+        op.matmat(np.ascontiguousarray(Vh[:5].T))
         op.mvm_sorted_device(V)
         G = op.to_grid_device(V[:3].contiguous())
         op.grid_mvm_device(G)
@@ -39,6 +42,7 @@ def main():
         op.mvm(Vh[:3])
         X, it, res, _ = op.minres_device(V, tol=1e-4, maxiter=12, check_every=5)
         op.minres_device(V, tol=1e-4, maxiter=6, check_every=5, precond='jacobi')
+        op.minres_lanczos_device(V, 8, tol=1e-4, maxiter=6, check_every=5)
         op.cg(Vh[:3], tol=1e-4, maxiter=6)
         op.grad_grams_device(X[0], V[1:], X[1:], None)
         torch.cuda.synchronize()
