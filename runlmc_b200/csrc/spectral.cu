@@ -516,6 +516,36 @@ __global__ void stage_twiddle_kernel(cplx* tab, int L, FftPlan pl, StageTw lay) 
 }  // namespace lmc
 #include "spectral_fused.cuh"
 #include "spectral_rows512.cuh"
+
+namespace lmc {
+// Tensor map over S_T seen as a matrix of doubles [rows = slab * 512 + pos][2 * xpitch]: boxes of 8 complex x 256
+// positions with the 128-byte swizzle.  cuTensorMapEncodeTiled is a host-side encoder of the driver API; it is
+// looked up at run time so that the library carries no link-time dependency on libcuda.
+static int rows512_tensor_map(CUtensorMap* map, const void* S, int xpitch, long rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        looked = true;
+    }
+    if (!encode) return 1;
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * xpitch, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)xpitch * sizeof(cplx)};
+    const cuuint32_t box[2] = {16, 256};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(S), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? 0 : 2;
+}
+}  // namespace lmc
 namespace lmc {
 LMC_FUSED_EXTERN(1) LMC_FUSED_EXTERN(2) LMC_FUSED_EXTERN(3) LMC_FUSED_EXTERN(4)
 LMC_FUSED_EXTERN(5) LMC_FUSED_EXTERN(6) LMC_FUSED_EXTERN(7) LMC_FUSED_EXTERN(8)
@@ -826,9 +856,24 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         r.spc = std::max(1, spc_env);
         r.tw1 = tw512_;
         dim3 grid((unsigned)(xpitch / 8), (unsigned)ceil_div(r.nslab, r.spc));
+        // transposed side by tensor copies (UTMALDG / UTMASTG) unless the driver's encoder is missing or
+        // LMC_NO_ROWS512_TMA2D asks for the 1-D bulk-copy kernels
+        static const bool tma2d = getenv("LMC_NO_ROWS512_TMA2D") == nullptr;
+        CUtensorMap tmap;
+        const bool use_tma = tma2d && rows512_tensor_map(&tmap, S, xpitch, (long)r.nslab * 512) == 0;
         {
             ProfScope prof(PROF_FFT_FWD_CONTIG, st);
-            rows512_fwd_kernel<<<grid, 256, kR512SmemFwd, st>>>(r);
+            if (use_tma) {
+                static bool attr_f = false;
+                if (!attr_f) {
+                    LMC_CHECK(cudaFuncSetAttribute(rows512_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kR512SmemFwdTma));
+                    attr_f = true;
+                }
+                rows512_fwd_tma_kernel<<<grid, 256, kR512SmemFwdTma, st>>>(r, tmap);
+            } else {
+                rows512_fwd_kernel<<<grid, 256, kR512SmemFwd, st>>>(r);
+            }
             count_launch();
             LMC_CHECK(cudaGetLastError());
         }
@@ -848,7 +893,17 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         LMC_TRY(rc);
         {
             ProfScope prof(PROF_FFT_INV_CONTIG, st);
-            rows512_inv_kernel<<<grid, 256, kR512SmemInv, st>>>(r);
+            if (use_tma) {
+                static bool attr_t = false;
+                if (!attr_t) {
+                    LMC_CHECK(cudaFuncSetAttribute(rows512_inv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kR512SmemInvTma));
+                    attr_t = true;
+                }
+                rows512_inv_tma_kernel<<<grid, 256, kR512SmemInvTma, st>>>(r, tmap);
+            } else {
+                rows512_inv_kernel<<<grid, 256, kR512SmemInv, st>>>(r);
+            }
             count_launch();
             LMC_CHECK(cudaGetLastError());
         }

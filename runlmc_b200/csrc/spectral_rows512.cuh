@@ -1,5 +1,8 @@
-// Transposing 2-D row passes for 512-point rows (128 < m_y <= 256), register-resident FFT + bulk
-// asynchronous copies (TMA, 1-D form) on both sides.  With spectral_col512.cuh they replace numpy's
+// Transposing 2-D row passes for 512-point rows (128 < m_y <= 256), register-resident FFT + TMA on both
+// sides: the rows of G by 1-D bulk copies, the transposed tiles of S_T by 2-D tensor copies
+// (rows512_*_tma_kernel below: cp.async.bulk.tensor.2d with the 128-byte swizzle, two copies per 64 KB tile;
+// the *_kernel variants without tensor maps move the same tiles as 512 bulk copies of 128 bytes and remain as
+// the fall-back when the driver's tensor-map encoder cannot be found).  With spectral_col512.cuh they replace numpy's
 // rfftn / irfftn inside BTTB.matvec (reference runlmc/linalg/bttb.py:144-148) for config-E geometries:
 //
 //   forward   G[slab][x][y]  (y contiguous)  ->  S_T[slab][pos][x]   (x contiguous)
@@ -21,6 +24,7 @@
 // holds frequency c + 16 (k2 + 16 h) (c = lane >> 1, h = lane & 1) with its true sign; the spectra the
 // column kernel multiplies with are stored in the same order along both axes (col512_spec2_kernel).
 #pragma once
+#include <cuda.h>
 #include "spectral_col512.cuh"
 
 namespace lmc {
@@ -218,6 +222,132 @@ __global__ void __launch_bounds__(256, 2) rows512_inv_kernel(const Rows512Args a
         }
         __syncthreads();                               // exchange buffers done before the next chunks land
     }
+}
+
+// ---------------------------------------------------------------------------
+// Inverse pass with the transposed tile fetched by two TENSOR copies (cp.async.bulk.tensor.2d, a 3-D view
+// would add nothing: S_T is [slab * 512 + pos][x] with a constant row pitch): box = 8 complex (128 B) x 256
+// positions, 128-byte swizzle, so the 64 KB tile lands dense in shared memory and a warp still picks its row
+// out of it without bank conflicts (chunk index XOR (pos & 7)).  One elected thread issues two copies per
+// slab instead of 512 bulk copies issued by all threads.
+// ---------------------------------------------------------------------------
+static const size_t kR512SmemInvTma = sizeof(cplx) * (size_t)(8 * kC512Line) + 16 + 1024;
+static_assert(8 * kC512Line >= 512 * 8, "exchange buffers cover the dense tile");
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(dst_smem)), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) rows512_inv_tma_kernel(const Rows512Args a,
+                                                                 const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ unsigned char smem_raw_t[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<unsigned long long>(smem_raw_t) + 1023ull) & ~1023ull);   // swizzle atoms are 1 KB
+    cplx* tile = reinterpret_cast<cplx*>(base);                   // [512][8] swizzled, then the exchange buffers
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + 8 * kC512Line);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int x0 = blockIdx.x * 8;
+    const long slab0 = (long)blockIdx.y * a.spc;
+    const int cnt = (int)min((long)a.spc, (long)a.nslab - slab0);
+    const bool row_ok = x0 + w < a.mx;
+    if (tid == 0) mbar_init(bar, 1);
+    const cplx w1 = a.tw1[lane];
+    __syncthreads();
+    cplx* buf = tile + w * kC512Line;
+    for (int t = 0; t < cnt; ++t) {
+        const long slab = slab0 + t;
+        if (tid == 0) {
+            fence_async_smem();                        // the warps' generic-proxy use of the tile precedes the copies
+            mbar_arrive_expect_tx(bar, 512u * 8u * (unsigned)sizeof(cplx));
+            tma_load_2d(tile, &tmap, 2 * x0, (int)(slab * 512), bar);
+            tma_load_2d(tile + 256 * 8, &tmap, 2 * x0, (int)(slab * 512 + 256), bar);
+        }
+        mbar_wait(bar, t & 1);
+        cplx x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int pos = k * 32 + lane;
+            x[k] = tile[pos * 8 + (w ^ (pos & 7))];
+        }
+        __syncthreads();                               // every warp has its row: the tile becomes the exchange buffers
+        warp_fft512_inv(x, buf, w1, lane);
+        if (row_ok) {
+            cplx* g = a.G_out + slab * a.g_slab + (long)(x0 + w) * a.my + lane;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (lane + 32 * r < a.my) g[32 * r] = x[r];
+        }
+        __syncthreads();                               // exchange buffers done before the next tile lands
+    }
+}
+
+// Forward pass, transposed side stored by two tensor copies from the swizzled dense tile.
+static const size_t kR512SmemFwdTma = sizeof(cplx) * (size_t)(8 * kC512Line + kR512In) + 16 + 1024;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int c0, int c1, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(
+                     reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) rows512_fwd_tma_kernel(const Rows512Args a,
+                                                                 const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ unsigned char smem_raw_t[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<unsigned long long>(smem_raw_t) + 1023ull) & ~1023ull);
+    cplx* tile = reinterpret_cast<cplx*>(base);        // the warps' exchange buffers, then [512][8] swizzled
+    cplx* in = tile + 8 * kC512Line;                   // [8][256]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(in + kR512In);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int x0 = blockIdx.x * 8;
+    const long slab0 = (long)blockIdx.y * a.spc;
+    const int cnt = (int)min((long)a.spc, (long)a.nslab - slab0);
+    const int nrows = min(8, a.mx - x0);
+    const unsigned row_bytes = (unsigned)a.my * (unsigned)sizeof(cplx);
+    const bool row_ok = w < nrows;
+    if (tid == 0) mbar_init(bar, 1);
+    const cplx w1 = a.tw1[lane];
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, row_bytes * nrows);
+        for (int r = 0; r < nrows; ++r)
+            bulk_g2s(in + r * 256, a.G_in + slab0 * a.g_slab + (long)(x0 + r) * a.my, row_bytes, bar);
+    }
+    cplx* buf = tile + w * kC512Line;
+    for (int t = 0; t < cnt; ++t) {
+        const long slab = slab0 + t;
+        mbar_wait(bar, t & 1);
+        cplx x[16];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            x[r] = (row_ok && lane + 32 * r < a.my) ? in[w * 256 + lane + 32 * r] : make_double2(0.0, 0.0);
+        if (tid == 0) bulk_wait_read();                // the previous slab's tensor stores have read the tile
+        __syncthreads();                               // rows are in registers, tile is free
+        if (tid == 0 && t + 1 < cnt) {
+            mbar_arrive_expect_tx(bar, row_bytes * nrows);
+            for (int r = 0; r < nrows; ++r)
+                bulk_g2s(in + r * 256, a.G_in + (slab + 1) * a.g_slab + (long)(x0 + r) * a.my, row_bytes, bar);
+        }
+        warp_fft512_fwd(x, buf, w1, lane);
+        __syncthreads();                               // every warp is done with its exchange buffer
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int pos = k * 32 + lane;
+            tile[pos * 8 + (w ^ (pos & 7))] = x[k];
+        }
+        fence_async_smem();                            // make the tile visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&tmap, 2 * x0, (int)(slab * 512), tile);
+            tma_store_2d(&tmap, 2 * x0, (int)(slab * 512 + 256), tile + 256 * 8);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all();
 }
 
 // specP2[q][l][p] = specL[q][old(k(l))][old(k(p))]: both axes in the position order of the register
