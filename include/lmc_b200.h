@@ -118,8 +118,8 @@ int lmc_mvm_sorted(lmc_op* op, const double* V_dev, long ld, int P, double* OUT_
  * column c < P -- numpy's C order for the [n, P] argument of Matrix.matmat (linalg/matrix.py:27-41), so a
  * caller holding such an array passes it as it is.  A point's columns are contiguous there: the scatter
  * stages them straight from the caller's rows and the permutation into the operator's point order costs
- * no pass of its own (column-major blocks pay two, lmc_mvm).  ldx, ldy >= P.  lmc_mvm_rows_host copies
- * the block in, multiplies and copies the result out (no pipelining: every column needs every row).  */
+ * no pass of its own (column-major blocks pay two, lmc_mvm).  ldx, ldy >= P.  lmc_mvm_rows_host pipelines
+ * chunks of columns (strided 2-D copies on the host side) through copy-in | product | copy-out.        */
 int lmc_mvm_rows(lmc_op* op, const double* X_dev, long ldx, int P, double* Y_dev, long ldy, void* stream);
 int lmc_mvm_rows_host(lmc_op* op, const double* X_host, long ldx, int P, double* Y_host, long ldy);
 /* unit-testable stages.  Grid vectors are [P][D*m], output-major (likelihood.py:30):

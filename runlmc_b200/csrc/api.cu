@@ -185,6 +185,10 @@ int lmc_mvm_rows(lmc_op* op, const double* X_dev, long ldx, int P, double* Y_dev
     return op_mvm_rows(op, X_dev, ldx, P, Y_dev, ldy, (cudaStream_t)stream);
 }
 
+// Host side of the point-major product.  Every column needs every row, so the pipeline runs over chunks of
+// COLUMNS like lmc_mvm_host: a chunk is a strided 2-D copy on the host side (rows of `chunk` doubles out of rows of
+// ldx) and a compact [n][chunk] block on the device; H2D copy | product | D2H copy on three streams with
+// double-buffered staging.
 int lmc_mvm_rows_host(lmc_op* op, const double* X_host, long ldx, int P, double* Y_host, long ldy) {
     LMC_REQUIRE(op, "null argument");
     if (P == 0) return 0;
@@ -193,20 +197,55 @@ int lmc_mvm_rows_host(lmc_op* op, const double* X_host, long ldx, int P, double*
     LMC_REQUIRE(op->Q > 0, "operator parameters not set (call lmc_op_set_params)");
     const long n = op->ps.n;
     LMC_CHECK(cudaDeviceSynchronize());   // shares the grid workspace with the stream-ordered entry points
-    const size_t need = (size_t)n * P;
-    if (need > op->rows_cap) {
-        cudaFree(op->rows_in); cudaFree(op->rows_out);
-        op->rows_in = op->rows_out = nullptr;
-        op->rows_cap = 0;
-        LMC_CHECK(cudaMalloc(&op->rows_in, sizeof(double) * need));
-        LMC_CHECK(cudaMalloc(&op->rows_out, sizeof(double) * need));
-        op->rows_cap = need;
+    // chunk width: 32 columns (one group of 16 pairs for the scatter, 256-byte row pieces for the copy engine)
+    // unless that needs more than 512 MB per staging buffer
+    int chunk = (int)std::max<long>(2, std::min<long>(32, (512L << 20) / (8 * n)));
+    chunk &= ~1;
+    if (P <= chunk + 1) chunk = P;        // a block of 32 k + 1 columns keeps its odd column in the last chunk
+    const size_t need = (size_t)(chunk + 1) * n;
+    if (!op->hs[0]) {
+        for (int i = 0; i < 3; ++i) LMC_CHECK(cudaStreamCreateWithFlags(&op->hs[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_in[i], cudaEventDisableTiming));
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_cmp[i], cudaEventDisableTiming));
+            LMC_CHECK(cudaEventCreateWithFlags(&op->ev_out[i], cudaEventDisableTiming));
+        }
     }
-    LMC_CHECK(cudaMemcpy2D(op->rows_in, sizeof(double) * P, X_host, sizeof(double) * ldx, sizeof(double) * P, n,
-                           cudaMemcpyHostToDevice));
-    LMC_TRY(op_mvm_rows(op, op->rows_in, P, P, op->rows_out, P, nullptr));
-    LMC_CHECK(cudaMemcpy2D(Y_host, sizeof(double) * ldy, op->rows_out, sizeof(double) * P, sizeof(double) * P, n,
-                           cudaMemcpyDeviceToHost));
+    if (need > op->stage_cap) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(op->stage_in[i]); cudaFree(op->stage_out[i]);
+            op->stage_in[i] = op->stage_out[i] = nullptr;
+        }
+        op->stage_cap = 0;
+        for (int i = 0; i < 2; ++i) {
+            LMC_CHECK(cudaMalloc(&op->stage_in[i], sizeof(double) * need));
+            LMC_CHECK(cudaMalloc(&op->stage_out[i], sizeof(double) * need));
+        }
+        op->stage_cap = need;
+    }
+    cudaStream_t s_in = op->hs[0], s_cmp = op->hs[1], s_out = op->hs[2];
+    int k = 0;
+    for (int c0 = 0; c0 < P; ++k) {
+        const int b = k & 1;
+        int cnt = std::min(chunk, P - c0);
+        if (P - c0 - cnt == 1) cnt += 1;   // never leave a single column for a chunk of its own
+        if (k >= 2) LMC_CHECK(cudaStreamWaitEvent(s_in, op->ev_cmp[b], 0));    // staging buffer consumed
+        LMC_CHECK(cudaMemcpy2DAsync(op->stage_in[b], sizeof(double) * cnt, X_host + c0, sizeof(double) * ldx,
+                                    sizeof(double) * cnt, n, cudaMemcpyHostToDevice, s_in));
+        LMC_CHECK(cudaEventRecord(op->ev_in[b], s_in));
+        LMC_CHECK(cudaStreamWaitEvent(s_cmp, op->ev_in[b], 0));
+        if (k >= 2) LMC_CHECK(cudaStreamWaitEvent(s_cmp, op->ev_out[b], 0));  // previous result copied out
+        LMC_TRY(op_mvm_rows(op, op->stage_in[b], cnt, cnt, op->stage_out[b], cnt, s_cmp));
+        LMC_CHECK(cudaEventRecord(op->ev_cmp[b], s_cmp));
+        LMC_CHECK(cudaStreamWaitEvent(s_out, op->ev_cmp[b], 0));
+        LMC_CHECK(cudaMemcpy2DAsync(Y_host + c0, sizeof(double) * ldy, op->stage_out[b], sizeof(double) * cnt,
+                                    sizeof(double) * cnt, n, cudaMemcpyDeviceToHost, s_out));
+        LMC_CHECK(cudaEventRecord(op->ev_out[b], s_out));
+        c0 += cnt;
+    }
+    LMC_CHECK(cudaStreamSynchronize(s_out));
+    LMC_CHECK(cudaStreamSynchronize(s_cmp));
+    LMC_CHECK(cudaStreamSynchronize(s_in));
     return 0;
 }
 

@@ -188,8 +188,6 @@ lmc_op::~lmc_op() {
     }
     for (int i = 0; i < 3; ++i)
         if (hs[i]) cudaStreamDestroy(hs[i]);
-    cudaFree(rows_in);
-    cudaFree(rows_out);
     cudaFree(spec);
     cudaFree(specL);
     cudaFree(specP);

@@ -55,9 +55,6 @@ struct lmc_op {
     double* stage_in[2] = {nullptr, nullptr};
     double* stage_out[2] = {nullptr, nullptr};
     size_t stage_cap = 0;   // doubles per staging buffer
-    double* rows_in = nullptr;   // device copies of a point-major host block (lmc_mvm_rows_host)
-    double* rows_out = nullptr;
-    size_t rows_cap = 0;
     // block-solver state vectors (MINRES: 8 [P][n] blocks, CG: 5), grow-only, kept between solves:
     // cudaMalloc/cudaFree of ~8 n P doubles per solve would cost as much as tens of iterations
     void* solver_ws = nullptr;

@@ -202,7 +202,9 @@ def test_wide_blocks_match_narrow_blocks_and_oracle(ndim):
     assert rel_err(op.mvm(V[:67]), narrow[:67]) < 1e-12
     X = np.ascontiguousarray(V[:67].T)
     assert rel_err(op.matmat(X), op.mvm(V[:67]).T) < 1e-12     # the column path cuts the block into chunks
-    assert np.array_equal(op.matmat(X), op.matmat_device(torch.as_tensor(X, device='cuda')).cpu().numpy())
+    # the host entry point pipelines chunks of 32 columns: other pair groups, same numbers to rounding
+    assert rel_err(op.matmat(X), op.matmat_device(torch.as_tensor(X, device='cuda')).cpu().numpy()) < 1e-12
+    assert np.array_equal(op.matmat(X[:, :33].copy()), op.matmat_device(torch.as_tensor(X[:, :33].copy(), device='cuda')).cpu().numpy())
     assert rel_err(op.matmat(np.asfortranarray(X)), op.matmat(X)) < 1e-12
     assert rel_err(op.matmat(X[:, :5]), op.matmat(X)[:, :5]) < 1e-12     # a strided view is copied first
 
