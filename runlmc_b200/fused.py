@@ -224,13 +224,17 @@ class FusedLMC:
         return out
 
     def matmat_device(self, X, out=None):
-        """X: torch float64 CUDA tensor [n, P], contiguous (point-major).  Stream ordered."""
+        """X: torch float64 CUDA tensor [n, P], point-major: unit stride along the columns, any row stride
+        >= P (a column slice of a wider block is fine).  Stream ordered."""
         torch = nat.require_cuda()
-        assert X.is_cuda and X.dtype == torch.float64 and X.is_contiguous() and X.shape[0] == self.n
-        if out is None:
-            out = torch.empty_like(X)
+        assert X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.shape[0] == self.n
         P = X.shape[1]
-        nat.check(nat.lib.lmc_mvm_rows(self._h, _dev(X), P, P, _dev(out), P, nat.current_stream_ptr()))
+        assert (P == 1 or X.stride(1) == 1) and X.stride(0) >= P
+        if out is None:
+            out = torch.empty((self.n, P), dtype=torch.float64, device=X.device)
+        assert (P == 1 or out.stride(1) == 1) and out.stride(0) >= P and out.shape == X.shape
+        nat.check(nat.lib.lmc_mvm_rows(self._h, _dev(X), X.stride(0), P, _dev(out), out.stride(0),
+                                        nat.current_stream_ptr()))
         return out
 
     def mvm_device(self, V, out=None):

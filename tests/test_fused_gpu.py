@@ -116,6 +116,13 @@ def test_point_major_blocks(name, P):
         assert rel_err(Y[:, c], ref.matvec(X[:, c])) < MVM_TOL
     assert np.array_equal(Y, op.mvm_device(Xd.t().contiguous()).cpu().numpy().T)
     assert np.array_equal(op.matmat(X), Y)
+    # a column slice of a wider block: row stride > P, rows that start 8 bytes off a 16-byte boundary
+    wide_in = torch.full((prob.n, P + 6), float('nan'), dtype=torch.float64, device='cuda')
+    wide_out = torch.full((prob.n, P + 4), float('nan'), dtype=torch.float64, device='cuda')
+    wide_in[:, 3:3 + P] = Xd
+    op.matmat_device(wide_in[:, 3:3 + P], wide_out[:, 1:1 + P])
+    assert np.array_equal(wide_out[:, 1:1 + P].cpu().numpy(), Y)
+    assert torch.isnan(wide_out[:, 0]).all() and torch.isnan(wide_out[:, 1 + P:]).all()     # nothing else written
 
 
 @pytest.mark.parametrize('name', ['lmc_A', 'lmc_2d', 'lmc_B'])
