@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpA
         for (int q = 0; q < 2; ++q) {
             const unsigned hv = __ballot_sync(0xffffffffu, have[q]);
             if (hv == 0) continue;                     // uniform over the warp
-            if (a.noise && !no_prefetch)
+            if (a.noise && !no_prefetch && np > 1)
                 prefetch_row_pieces8(so[q], hv, gb, g, 2 * (pbase + g), pbase + g < pair_hi, xin, a.ldr);
             double acc[GP][2];
 #pragma unroll
@@ -1252,6 +1252,23 @@ __global__ void __launch_bounds__(256, 2) from_grid_2d_rows_kernel(const InterpA
                 }
                 acc[p][0] = r0s;
                 acc[p][1] = r1s;
+            }
+            if (np == 1) {
+                // a pass with a single pair (the odd last pair of 8 k + 1): every thread stores its own point's
+                // one or two values, no transpose (uniform over the CTA)
+                if (have[q]) {
+                    const int cA1 = 2 * pbase;
+                    const bool okB1 = cA1 + 1 < a.ncols;
+                    const long row = so[q];
+                    double v0 = acc[0][0], v1 = acc[0][1];
+                    if (a.noise) {
+                        v0 = fma(nz, __ldcs(xin + row * a.ldr + cA1), v0);
+                        if (okB1) v1 = fma(nz, __ldcs(xin + row * a.ldr + cA1 + 1), v1);
+                    }
+                    __stcs(yout + row * a.ldo + cA1, v0);
+                    if (okB1) __stcs(yout + row * a.ldo + cA1 + 1, v1);
+                }
+                continue;
             }
             lane_group_transpose8(acc, g);     // acc[i] now belongs to point (gb + i), pair pbase + g
             const int pair = pbase + g;
