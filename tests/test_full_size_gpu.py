@@ -55,9 +55,17 @@ def test_stated_size_product_matches_oracle(stated):
         want = ref.matvec(V[c])
         assert rel_err(KV[c].cpu().numpy(), want) < MVM_TOL
         assert rel_err(KVs[c].cpu().numpy(), want[op.perm()]) < MVM_TOL
-    # the host-buffer entry point (chunked copy/compute pipeline) on the same block
+    # the same block point-major ([n, P], the layout bench.py times): row staging in the scatter, row-writing gather
+    KVr = op.matmat_device(Vd.t().contiguous())
+    assert torch.equal(KVr.t(), KV)                       # bit for bit the column-major entry point
+    for c in cols:
+        assert rel_err(KVr[:, c].cpu().numpy(), ref.matvec(V[c])) < MVM_TOL
+    # the host-buffer entry points (chunked copy/compute pipelines) on the same block
     got = op.mvm(V[[0, 1, V.shape[0] - 1]])
     for g, c in zip(got, (0, 1, V.shape[0] - 1)):
+        assert rel_err(g, ref.matvec(V[c])) < MVM_TOL
+    got = op.matmat(np.ascontiguousarray(V[[0, 1, V.shape[0] - 1]].T))
+    for g, c in zip(got.T, (0, 1, V.shape[0] - 1)):
         assert rel_err(g, ref.matvec(V[c])) < MVM_TOL
 
 
