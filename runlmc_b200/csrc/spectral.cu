@@ -852,8 +852,11 @@ int SpectralEngine::apply_fused(cplx* G, cplx* S, int npairs, int D, int Q, cons
         r.G_in = G; r.G_out = G; r.ST = S;
         r.g_slab = e.grid_pitch; r.st_slab = (long)e.mt[1] * xpitch;
         r.mx = e.m[0]; r.my = e.m[1]; r.xpitch = xpitch; r.nslab = npairs * D;
-        static const int spc_env = getenv("LMC_ROWS512_SPC") ? atoi(getenv("LMC_ROWS512_SPC")) : 4;
-        r.spc = std::max(1, spc_env);
+        // slabs per CTA (set-up once, the forward pass requests its next rows early): 8 when that still leaves
+        // ~8 waves of CTAs (config E, 129 columns: 0.357 -> 0.346 / 0.365 -> 0.357 ms), else 4
+        static const int spc_env = getenv("LMC_ROWS512_SPC") ? atoi(getenv("LMC_ROWS512_SPC")) : 0;
+        const long tiles = (long)r.nslab * (xpitch / 8);
+        r.spc = spc_env > 0 ? spc_env : (tiles >= 148L * 2 * 8 * 8 ? 8 : 4);
         r.tw1 = tw512_;
         dim3 grid((unsigned)(xpitch / 8), (unsigned)ceil_div(r.nslab, r.spc));
         // transposed side by tensor copies (UTMALDG / UTMASTG) unless the driver's encoder is missing or

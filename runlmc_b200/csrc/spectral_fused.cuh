@@ -280,7 +280,7 @@ static inline bool use_col512(const FusedArgs& a) {
 
 template <int D, class MIX>
 static int launch_col512_kernel(const FusedArgs& a, const MIX& m, int npairs, cudaStream_t st) {
-    static const int ppc_env = getenv("LMC_COL512_PPC") ? atoi(getenv("LMC_COL512_PPC")) : 4;
+    static const int ppc_env = getenv("LMC_COL512_PPC") ? atoi(getenv("LMC_COL512_PPC")) : 8;   // 4 -> 8: 1.435 -> 1.412 ms at config E
     const size_t smem = sizeof(cplx) * (size_t)(D * kC512Line);
     constexpr int MINB = D <= 10 ? 2 : 1;
     static bool attr = false;
