@@ -121,8 +121,9 @@ class ApproxLMCLikelihood(LMCLikelihood):
             else:
                 extra = [t for ts in self.materialized_grads for t in ts]
                 counts = [len(t) for t in self.materialized_grads]
-            quad, trace, nquad, ntrace = fused.grad_grams(
-                d.alpha, np.asarray(d._rs, dtype=np.float64), np.asarray(d._inv_rs), extra)
+            a, R, Rinv = d._dev()          # already on the device when the service solved with a fused operator
+            quad, trace, nquad, ntrace = fused.grad_grams_device(a[0], R if len(R) else None,
+                                                                  Rinv if len(R) else None, extra)
             self._fused_grads = assemble_gradients(
                 fk.coreg_vecs, fk.coreg_mats(), counts, d._n_it, quad, trace, nquad, ntrace)
         return self._fused_grads

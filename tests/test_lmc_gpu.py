@@ -378,3 +378,44 @@ def test_lanczos_record_and_stochastic_logdet():
     assert abs(deriv.log_det_K - est) < 1e-9 * abs(est) and abs(deriv.log_det_K_stderr - err) < 1e-6 * err
     plain = StochasticDerivService(None, None, len(probes), 1e-4).generate(K, prob.y, rs=probes)
     assert plain.log_det_K is None and np.array_equal(plain.alpha, deriv.alpha)
+
+
+def test_device_probes_and_device_resident_derivative():
+    """The service keeps right-hand sides and solutions on the device (host copies appear only when read),
+    and can draw its Rademacher probes there: reproducible under torch's seed, +-1, and an estimator of the
+    same gradient (checked against the exact trace term on a small problem)."""
+    import torch
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.lmc.likelihood import ApproxLMCLikelihood
+    from runlmc_b200.lmc.stochastic_deriv import StochasticDerivService
+    from runlmc_b200.util.inline_pool import InlinePool
+    from test_oracle_golden import oracle_operator
+    prob, g = golden_problem('lmc_A')
+    fk, dists, interps, ad = build(prob)
+    K, _ = gen_grid_kernel(fk, dists, interps, prob.lens)
+    N = 64
+
+    def run(seed):
+        torch.manual_seed(seed)
+        svc = StochasticDerivService(None, InlinePool(None), N, 1e-6, device_probes=True)
+        return ApproxLMCLikelihood(fk, K, dists, interps, prob.Ys, svc)
+
+    lik = run(3)
+    d = lik.deriv
+    assert d._rs_host is None and d._inv_rs_host is None          # nothing copied to the host yet
+    noise = lik.noise_gradient()
+    again = run(3).noise_gradient()
+    np.testing.assert_array_equal(noise, again)                     # same seed, same probes
+    assert not np.array_equal(noise, run(4).noise_gradient())
+    rs = d._rs
+    assert rs.shape == (N, prob.n) and set(np.unique(rs)) == {-1.0, 1.0}
+    assert len(d._inv_rs) == N and rel_err(d.alpha, g['alpha']) < 1e-5
+    # exact noise gradient from the dense oracle operator: 0.5 (alpha_d' alpha_d - tr_d(K^-1))
+    _, ref = oracle_operator(prob)
+    Kinv = np.linalg.inv(ref.dense())
+    alpha = Kinv.dot(prob.y)
+    off = np.cumsum([0] + list(prob.lens))
+    exact = np.array([0.5 * (alpha[a:b].dot(alpha[a:b]) - np.trace(Kinv[a:b, a:b])) for a, b in zip(off, off[1:])])
+    # Hutchinson error of the trace term: ~ sqrt(2 / N) ||K^-1_dd||_F per output
+    slack = np.array([4 * 0.5 * np.sqrt(2.0 / N) * np.linalg.norm(Kinv[a:b, a:b]) for a, b in zip(off, off[1:])])
+    assert np.all(np.abs(noise - exact) < slack + 1e-6 * np.abs(exact))

@@ -87,6 +87,46 @@ def reference_call_sequence(name='E'):
         name, time.perf_counter() - t, W.nnz))
 
 
+def reference_gradient_step(name='E'):
+    """One optimiser step the way the reference's model takes it (interpolated_llgp.py:192-207): gen_grid_kernel,
+    ApproxLMCLikelihood(..., StochasticDerivService) -- probes drawn inside generate() -- and the four gradient
+    families, on the well-conditioned hyper-parameters of bench.py's converging gradient row."""
+    from runlmc_b200.approx.interpolation import multi_interpolant
+    from runlmc_b200.lmc.functional_kernel import FunctionalKernel
+    from runlmc_b200.lmc.grid_kernel import gen_grid_kernel
+    from runlmc_b200.lmc.likelihood import ApproxLMCLikelihood
+    from runlmc_b200.lmc.stochastic_deriv import StochasticDerivService
+    from runlmc_b200.util.inline_pool import InlinePool
+    kw = {'E': dict(cells_per_lengthscale=1.5, eps=1.0, noise_scale=300.0),
+          'D': dict(cells_per_lengthscale=2, eps=1.0, noise_scale=100.0)}.get(name, dict(cells_per_lengthscale=4))
+    prob = synthetic.make_problem(name, seed=1234, **kw)
+    fk = FunctionalKernel(D=prob.D, lmc_kernels=[kern.RBF(g) for g in prob.gammas], lmc_ranks=[1] * prob.Q)
+    fk.noise = prob.noise
+    fk.coreg_vecs = prob.coreg_vecs
+    fk.coreg_diags = prob.coreg_diags
+    fk.set_input_dim(prob.ndim)
+    ad = tuple(range(prob.ndim))
+    W = multi_interpolant(prob.Xs, *prob.grids)
+    WT = W.transpose().tocsr()
+    for label, dev_probes in (('probes from numpy (reference stream)', False), ('probes drawn on the device', True),
+                              ('probes from numpy (reference stream)', False), ('probes drawn on the device', True)):
+        np.random.seed(1)
+        torch.manual_seed(1)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        K, _ = gen_grid_kernel(fk, {ad: prob.dists}, {ad: (W, WT)}, prob.lens)
+        svc = StochasticDerivService(None, InlinePool(None), prob.N, 1e-4, device_probes=dev_probes)
+        lik = ApproxLMCLikelihood(fk, K, {ad: prob.dists}, {ad: (W, WT)}, prob.Ys, svc)
+        grads = fk.update_gradient(lik)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        print('%s one optimiser step through the reference call sequence, %s: %.3f s (noise gradient[0] = %.6g)'
+              % (name, label, dt, grads['noise'][0]))
+        del lik, K, svc
+
+
 if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'E'
     main()
-    reference_call_sequence(sys.argv[1] if len(sys.argv) > 1 else 'E')
+    reference_call_sequence(which)
+    reference_gradient_step(which)
