@@ -281,9 +281,12 @@ __global__ void __launch_bounds__(256, CAP <= 256 ? 4 : 2) to_grid_1d_v3_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw1[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw1);
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x % a.tiles;
-    const int d = blockIdx.x / a.tiles;
-    const int grp = blockIdx.y;
+    // point-major blocks: the pair groups of one tile are neighbours in launch order (group index fastest), so
+    // the 16 G-byte pieces they take out of the same rows meet in L2 instead of being fetched from DRAM per group
+    const int bt = ROWS ? blockIdx.y : blockIdx.x;
+    const int tile = bt % a.tiles;
+    const int d = bt / a.tiles;
+    const int grp = ROWS ? blockIdx.x : blockIdx.y;
     const int col0 = 2 * G * grp;
     if (!group_active(a, col0, 2 * G)) return;
     const int ncol = min(2 * G, a.ncols - col0);
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(256) from_grid_1d_rows_kernel(const InterpArgs
     const long pstride = (long)a.D * a.grid_pitch;
     const int lane = threadIdx.x & 31, gb = lane & ~7, g = lane & 7;
     for (int pc = pair0; pc < pair1; pc += 8) {
+        if (a.noise) prefetch_row_pieces8(so, hv, gb, g, 2 * (pc + g), pc + g < pair1, a.in_rows, a.ldr);
         double acc[8][2];
 #pragma unroll
         for (int hf = 0; hf < 8; hf += 4) {
@@ -1600,8 +1604,9 @@ static int to_grid_launch(const PointSet& ps, const ColumnView& cv, cplx* G, Sca
         a.tiles = ceil_div(ps.m[0], TC);
         dim3 grid((unsigned)(a.tiles * ps.D), (unsigned)ceil_div(npairs, G1));
         if (a.in_rows) {
-            if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S, true><<<grid, 256, sizeof(SmemS), st>>>(a);
-            else to_grid_1d_v3_kernel<G1, CAP1, true><<<grid, 256, sizeof(Smem), st>>>(a);
+            const dim3 grid_r(grid.y, grid.x);      // group index fastest
+            if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S, true><<<grid_r, 256, sizeof(SmemS), st>>>(a);
+            else to_grid_1d_v3_kernel<G1, CAP1, true><<<grid_r, 256, sizeof(Smem), st>>>(a);
         } else {
             if (cap_sel == CAP1S) to_grid_1d_v3_kernel<G1, CAP1S, false><<<grid, 256, sizeof(SmemS), st>>>(a);
             else to_grid_1d_v3_kernel<G1, CAP1, false><<<grid, 256, sizeof(Smem), st>>>(a);
