@@ -232,3 +232,40 @@ def test_kernel_formulas_and_parameter_gradients():
         assert len(grads) == len(params) == len(make(*params).param_values())
         for i, g in enumerate(grads):
             np.testing.assert_allclose(g, fd(make, params, i), rtol=2e-6, atol=2e-8)
+
+
+def test_logdet_quadrature_host_side():
+    """The host half of the stochastic log-determinant (eigen-decomposition of the recorded tridiagonals) against
+    the oracle's quadrature on coefficients recorded by the oracle's MINRES loop, including a column that stopped
+    early and a record shorter than the solve."""
+    from oracle import lmc_oracle as orc
+    from runlmc_b200.approx.logdet import quadrature_terms
+    rng = np.random.default_rng(4)
+    n = 60
+    A = rng.standard_normal((n, n))
+    A = A.dot(A.T) + n * np.eye(n)
+    recs, want = [], []
+    for k in (9, 5):
+        z = rng.integers(0, 2, n) * 2.0 - 1.0
+        rec = []
+        orc.minres(A.dot, z, 1e-30, k, record=rec)
+        recs.append(rec)
+        want.append(orc.lanczos_quadrature_logdet(rec[0], rec[1:]))
+    K = 12
+    tri = np.zeros((2, K, 2))
+    for c, rec in enumerate(recs):
+        tri[c, :len(rec) - 1] = np.array(rec[1:])
+    beta1 = np.array([r[0] for r in recs])
+    iters = np.array([len(r) - 1 for r in recs])
+    got = quadrature_terms(tri, beta1, iters)
+    assert np.allclose(got, want, rtol=1e-12)
+    # a record of 4 steps of the 9-step solve uses the leading 4 x 4 tridiagonal
+    short = quadrature_terms(tri[:1, :4], beta1[:1], iters[:1])
+    assert np.isclose(short[0], orc.lanczos_quadrature_logdet(recs[0][0], recs[0][1:5]), rtol=1e-12)
+    # a zero right-hand side (no iterations) contributes nothing
+    assert quadrature_terms(tri[:1], beta1[:1], np.array([0]))[0] == 0.0
+    # Gauss quadrature with n nodes of a log-like integrand: sanity against the exact value for this small matrix
+    exact = np.linalg.slogdet(A)[1]
+    probes = rng.integers(0, 2, (200, n)) * 2.0 - 1.0
+    est, _ = orc.stochastic_logdet(A.dot, probes, 1e-12, n)
+    assert abs(est - exact) < 0.02 * abs(exact)
